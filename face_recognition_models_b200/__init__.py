@@ -1,0 +1,16 @@
+"""B200-native large-margin cosine-softmax head (drop-in for main_code/utils/criterion.py heads).
+
+Public API:
+  ArcFace, CosFace, SphereFace, MV_Softmax, CurricularFace, AdaFace, ElasticCosFace, ElasticArcFace,
+  MagFace             - nn.Modules with the reference constructor signatures
+  FusedOutput         - result of ``head.fused_loss(feats, labels)``
+  ShardedMarginHead   - class-sharded (Partial-FC style) head over torch.distributed / NCCL
+All compute runs in libmargin_head.so (hand-written sm_100a CUDA behind a C ABI, include/margin_head.h).
+"""
+from .heads import (AdaFace, ArcFace, CosFace, CurricularFace, ElasticArcFace, ElasticCosFace, FusedOutput,
+                    HEAD_CLASSES, MagFace, MV_Softmax, SphereFace)
+from .functional import HeadEngine, ShardInfo
+from . import _lib
+
+__all__ = ["AdaFace", "ArcFace", "CosFace", "CurricularFace", "ElasticArcFace", "ElasticCosFace", "FusedOutput",
+           "HEAD_CLASSES", "MagFace", "MV_Softmax", "SphereFace", "HeadEngine", "ShardInfo", "_lib"]

@@ -1,0 +1,108 @@
+"""ctypes binding of libmargin_head.so (C ABI declared in include/margin_head.h).
+
+There is no CPU fallback: if the shared library is missing or the device is not sm_100, every
+entry point raises.  The library is built in-tree by ``__graft_entry__.build()`` (or
+``make -C face_recognition_models_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmargin_head.so")
+
+_lib: Optional[C.CDLL] = None
+
+
+class MhConfig(C.Structure):
+    """Mirror of ``mh_config`` in include/margin_head.h."""
+    _fields_ = [
+        ("family", C.c_int32), ("easy_margin", C.c_int32), ("sphere_m", C.c_int32), ("plus", C.c_int32),
+        ("s", C.c_float), ("m", C.c_float), ("mv_weight", C.c_float), ("momentum", C.c_float),
+        ("h", C.c_float), ("t_alpha", C.c_float),
+        ("l_margin", C.c_float), ("u_margin", C.c_float), ("l_a", C.c_float), ("u_a", C.c_float),
+        ("sphere_lambda", C.c_float), ("reserved", C.c_float),
+    ]
+
+
+# enums of include/margin_head.h
+FAMILY = dict(arcface=0, cosface=1, sphereface=2, mv_am=3, mv_arc=4, curricularface=5, adaface=6,
+              elastic_cos=7, elastic_arc=8, magface=9)
+LAYOUT_CD, LAYOUT_DC = 0, 1
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+RP = dict(SCALE=0, THR=1, ZT=2, DZT=3, T=4, DZT_DN=5, DLG_DN=6, NORMS=7)
+RP_PLANES = 8
+ST_PLANES = 4
+RO = dict(LSE2=0, LOSS=1, CNT=2, AUX0=3, AUX1=4)
+RO_PLANES = 5
+STATE_FLOATS = 8
+MERGE_BLOCKS = 64
+TILE = 128
+NTILE = 256
+D = 512
+
+_vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int
+_cfgp = C.POINTER(MhConfig)
+
+# name -> argtypes; every function returns int (mh_status) unless listed in _RESTYPES
+SIGNATURES = {
+    "mh_device_check": [],
+    "mh_prologue_w": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp],
+    "mh_prologue_x": [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mh_row_params": [_cfgp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
+    "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
+    "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "mh_tc_backward_dx": [_vp, _i64, _i64, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mh_tc_backward_dw": [_vp, _i64, _i64, _vp, _vp, _vp],
+    "mh_sgemm_strided": [_i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp],
+    "mh_dense_forward": [_cfgp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mh_dense_backward_dc": [_cfgp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mh_merge_stats": [_vp, _i64, _i64, _i64, _vp, _vp, _vp],
+    "mh_finalize_rows": [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp],
+    "mh_norm_backward_x": [_vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _vp],
+    "mh_norm_backward_w": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
+}
+_RESTYPES = {"mh_version": C.c_char_p, "mh_last_error": C.c_char_p, "mh_fwd_num_tiles": C.c_int64}
+EXPORTED = sorted(list(SIGNATURES) + ["mh_version", "mh_last_error", "mh_fwd_num_tiles"])
+
+
+class MarginHeadError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MarginHeadError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the margin head.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.mh_version.restype = C.c_char_p
+    lib.mh_version.argtypes = []
+    lib.mh_last_error.restype = C.c_char_p
+    lib.mh_last_error.argtypes = []
+    lib.mh_fwd_num_tiles.restype = C.c_int64
+    lib.mh_fwd_num_tiles.argtypes = [C.c_int64]
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().mh_last_error().decode("utf-8", "replace")
+        raise MarginHeadError(f"{what} failed (status {status}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point and raise MarginHeadError on a non-zero status."""
+    lib = load()
+    check(getattr(lib, name)(*args), name)

@@ -1,0 +1,91 @@
+// Shared helpers for the margin-head kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/margin_head.h"
+
+#define MH_LOG2E 1.4426950408889634f
+#define MH_LN2 0.6931471805599453f
+
+void mh_set_error(const char* fmt, ...);
+
+#define MH_CHECK_ARG(cond, msg)                              \
+  do {                                                       \
+    if (!(cond)) {                                           \
+      mh_set_error("%s: %s", __func__, msg);                 \
+      return MH_ERR_ARG;                                     \
+    }                                                        \
+  } while (0)
+
+#define MH_CUDA_OK(expr)                                                            \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      mh_set_error("%s: %s -> %s", __func__, #expr, cudaGetErrorString(_e));        \
+      return MH_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+#define MH_LAUNCH_OK()                                                              \
+  do {                                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      mh_set_error("%s: launch failed: %s", __func__, cudaGetErrorString(_e));      \
+      return MH_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+// Device copy of the hyper-parameters + derived constants, passed by value to kernels.
+struct MhParams {
+  int family;
+  int easy_margin;
+  int sphere_m;
+  int hard_kind;          // 0 none, 1 MV (c>thr -> a*c+b), 2 Curricular (c>thr -> c*(t_buf+c), t_buf read from state)
+  float s, m;
+  float cos_m, sin_m, th, mm;
+  float lo, hi;           // clamp bounds on the raw cosine (ArcFace: -inf/+inf)
+  float hard_a, hard_b;
+  float momentum, h, t_alpha;
+  float l_margin, u_margin, l_a, u_a;
+  float sphere_lambda;
+  int scale_is_norm;      // SphereFace: logit scale is |x_i|
+};
+
+MhParams mh_make_params(const mh_config* c);
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Element transform shared by every B x C kernel (tensor-core and exact paths).
+// raw cosine -> (u, du/dcos_raw, c_clamped); the row scale multiplies outside.
+// MV-Softmax criterion.py:433-435, CurricularFace criterion.py:559,575, clamps per family.
+struct ElemOut { float u, du, c; };
+__device__ __forceinline__ ElemOut mh_elem(float raw, float lo, float hi, int hard_kind, float thr,
+                                           float ha, float hb) {
+  ElemOut o;
+  float c = fminf(fmaxf(raw, lo), hi);
+  float inside = (raw >= lo && raw <= hi) ? 1.f : 0.f;
+  o.c = c;
+  if (hard_kind == 1 && c > thr) {
+    o.u = fmaf(ha, c, hb);
+    o.du = ha * inside;
+  } else if (hard_kind == 2 && c > thr) {
+    o.u = c * (ha + c);
+    o.du = (ha + 2.f * c) * inside;
+  } else {
+    o.u = c;
+    o.du = inside;
+  }
+  return o;
+}

@@ -1,0 +1,444 @@
+// HBM-bound prologues: L2-normalise class centres and embeddings, gather the target cosine,
+// and compute the per-row margin terms.  Replaces F.normalize / torch.norm / the target gather
+// of the reference heads (criterion.py:65,95,173-174,263-264,400-404,417,538-542,552,860-864,...).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// prologue_w, layout CD: W [C, 512] row-major. One warp per class; 16 B vector loads, 8 B bf16 stores.
+// Algorithmic bytes per class: 2048 read + 1024 bf16 write (+2048 optional fp32 copy) + 4.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prologue_w_cd_kernel(const float* __restrict__ W, int64_t C, int64_t ld,
+                                                            __nv_bfloat16* __restrict__ what, int64_t C_pad,
+                                                            float* __restrict__ what32, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= C_pad) return;
+  uint2* dst = reinterpret_cast<uint2*>(what + row * MH_D);
+  if (row >= C) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = make_uint2(0u, 0u);
+    return;
+  }
+  const float4* src = reinterpret_cast<const float4*>(W + row * ld);
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = __ldg(src + lane + 32 * k);
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0) inv_norm[row] = inv;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 o = make_float4(v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    dst[lane + 32 * k] = pk;
+    if (what32) reinterpret_cast<float4*>(what32 + row * MH_D)[lane + 32 * k] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue_w, layout DC: W [512, C] (class index contiguous). A block stages a [512 x 32-class] slab
+// in shared memory with coalesced 128 B row reads, reduces column norms, and writes the transposed,
+// normalised bf16 rows (coalesced along d). One read of W, one write of w_hat.
+// ------------------------------------------------------------------------------------------------
+#define PW_TC 32
+__global__ void __launch_bounds__(256) prologue_w_dc_kernel(const float* __restrict__ W, int64_t C, int64_t ld,
+                                                            __nv_bfloat16* __restrict__ what, int64_t C_pad,
+                                                            float* __restrict__ what32, float* __restrict__ inv_norm) {
+  extern __shared__ float slab[];            // [512][33]
+  __shared__ float part[8][PW_TC];
+  __shared__ float invs[PW_TC];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * PW_TC;
+  const int64_t c = c0 + tx;
+  float ss = 0.f;
+  for (int d = ty; d < MH_D; d += 8) {
+    float v = (c < C) ? __ldg(W + (int64_t)d * ld + c) : 0.f;
+    slab[d * 33 + tx] = v;
+    ss += v * v;
+  }
+  part[ty][tx] = ss;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][tx];
+    float inv = 1.f / fmaxf(sqrtf(t), 1e-12f);
+    invs[tx] = inv;
+    if (c < C) inv_norm[c] = inv;
+  }
+  __syncthreads();
+  // each warp writes 4 class rows; lanes run along d (4 consecutive d per lane per step)
+  for (int r = ty; r < PW_TC; r += 8) {
+    const int64_t row = c0 + r;
+    if (row >= C_pad) continue;
+    const float inv = (row < C) ? invs[r] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int d = (tx + 32 * k) * 4;
+      float4 o = make_float4(slab[(d + 0) * 33 + r] * inv, slab[(d + 1) * 33 + r] * inv,
+                             slab[(d + 2) * 33 + r] * inv, slab[(d + 3) * 33 + r] * inv);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      reinterpret_cast<uint2*>(what + row * MH_D)[tx + 32 * k] = pk;
+      if (what32 && row < C) reinterpret_cast<float4*>(what32 + row * MH_D)[tx + 32 * k] = o;
+    }
+  }
+}
+
+// zero the padding rows [C, C_pad) that no DC block covers
+__global__ void zero_pad_rows_kernel(__nv_bfloat16* what, int64_t row0, int64_t row1) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (row1 - row0) * MH_D;
+  if (i < n) what[row0 * MH_D + i] = __float2bfloat16(0.f);
+}
+
+extern "C" int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, void* w_hat_bf16, int64_t C_pad,
+                             float* w_hat32, float* inv_norm, void* stream) {
+  MH_CHECK_ARG(W && w_hat_bf16 && inv_norm, "null pointer");
+  MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % MH_TILE == 0, "C_pad must be a multiple of 128 and >= C");
+  MH_CHECK_ARG(((uintptr_t)W & 15) == 0 && ((uintptr_t)w_hat_bf16 & 15) == 0, "pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout == MH_LAYOUT_CD) {
+    MH_CHECK_ARG(ld >= MH_D && ld % 4 == 0, "CD layout needs ld >= 512 and ld % 4 == 0");
+    dim3 grid((unsigned)((C_pad + 7) / 8));
+    prologue_w_cd_kernel<<<grid, 256, 0, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
+  } else if (layout == MH_LAYOUT_DC) {
+    MH_CHECK_ARG(ld >= C, "DC layout needs ld >= C");
+    static bool attr_set = false;
+    const int smem = MH_D * 33 * sizeof(float);
+    if (!attr_set) {
+      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    dim3 grid((unsigned)((C + PW_TC - 1) / PW_TC));
+    prologue_w_dc_kernel<<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
+    const int64_t covered = (int64_t)grid.x * PW_TC;
+    if (covered < C_pad) {
+      int64_t n = (C_pad - covered) * MH_D;
+      zero_pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)w_hat_bf16, covered, C_pad);
+    }
+  } else {
+    MH_CHECK_ARG(false, "unknown layout");
+  }
+  MH_LAUNCH_OK();
+  return MH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue_x: one warp per embedding row. Reads x once (4*512 B in fp32), gathers the target class
+// centre (4*512 B), writes x_hat bf16 (1 KB) + fp32 copy + three scalars.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p, int64_t i);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p, int64_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p, int64_t i) { return __half2float(p[i]); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x, int64_t B, int64_t B_pad,
+                                                         const int64_t* __restrict__ labels, const float* __restrict__ W,
+                                                         int layout, int64_t C, int64_t ld, int64_t c_offset,
+                                                         const float* __restrict__ inv_norm,
+                                                         __nv_bfloat16* __restrict__ xhat, float* __restrict__ xhat32,
+                                                         float* __restrict__ xnorm, float* __restrict__ t_raw,
+                                                         int32_t* __restrict__ label_local) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= B_pad) return;
+  if (row >= B) {
+    for (int k = lane; k < MH_D / 2; k += 32) reinterpret_cast<uint32_t*>(xhat + row * MH_D)[k] = 0u;
+    if (lane == 0) label_local[row] = -1;
+    return;
+  }
+  float v[16];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float f = load_as_float<T>(x, row * MH_D + (lane + 32 * k) * 4 + e);
+      v[k * 4 + e] = f;
+      ss += f * f;
+    }
+  }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float inv = 1.f / fmaxf(nrm, 1e-12f);
+  const int64_t y = labels[row] - c_offset;
+  const bool owned = (y >= 0 && y < C);
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 o = make_float4(v[k * 4 + 0] * inv, v[k * 4 + 1] * inv, v[k * 4 + 2] * inv, v[k * 4 + 3] * inv);
+    const int d = (lane + 32 * k) * 4;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    reinterpret_cast<uint2*>(xhat + row * MH_D)[lane + 32 * k] = pk;
+    reinterpret_cast<float4*>(xhat32 + row * MH_D)[lane + 32 * k] = o;
+    if (owned) {
+      if (layout == MH_LAYOUT_CD) {
+        float4 w = __ldg(reinterpret_cast<const float4*>(W + y * ld + d));
+        dot += o.x * w.x + o.y * w.y + o.z * w.z + o.w * w.w;
+      } else {
+        dot += o.x * __ldg(W + (int64_t)(d + 0) * ld + y) + o.y * __ldg(W + (int64_t)(d + 1) * ld + y) +
+               o.z * __ldg(W + (int64_t)(d + 2) * ld + y) + o.w * __ldg(W + (int64_t)(d + 3) * ld + y);
+      }
+    }
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    xnorm[row] = nrm;
+    t_raw[row] = owned ? dot * inv_norm[y] : 0.f;
+    label_local[row] = owned ? (int32_t)y : -1;
+  }
+}
+
+extern "C" int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pad, const int64_t* labels,
+                             const float* W, int layout, int64_t C, int64_t ld, int64_t c_offset,
+                             const float* inv_norm, void* x_hat_bf16, float* x_hat32, float* xnorm, float* t_raw,
+                             int32_t* label_local, void* stream) {
+  MH_CHECK_ARG(x && labels && W && inv_norm && x_hat_bf16 && x_hat32 && xnorm && t_raw && label_local, "null pointer");
+  MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % MH_TILE == 0, "B_pad must be a multiple of 128 and >= B");
+  MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
+  MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)W & 15) == 0), "CD weight must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((B_pad + 7) / 8));
+  __nv_bfloat16* xh = (__nv_bfloat16*)x_hat_bf16;
+  if (x_dtype == MH_F32)
+    prologue_x_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
+                                                   inv_norm, xh, x_hat32, xnorm, t_raw, label_local);
+  else if (x_dtype == MH_BF16)
+    prologue_x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, B_pad, labels, W, layout, C, ld,
+                                                           c_offset, inv_norm, xh, x_hat32, xnorm, t_raw, label_local);
+  else if (x_dtype == MH_F16)
+    prologue_x_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
+                                                    inv_norm, xh, x_hat32, xnorm, t_raw, label_local);
+  else
+    MH_CHECK_ARG(false, "unknown x dtype");
+  MH_LAUNCH_OK();
+  return MH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row_params: per-row margin terms and batch-global state. One block; B is a few thousand at most.
+// Mirrors the scalar/vector parts of every reference forward (file:line beside each branch).
+// ------------------------------------------------------------------------------------------------
+__device__ double block_sum_dd(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[k];
+  return t;
+}
+
+__device__ __forceinline__ float cheb(int m, float c) {  // criterion.py:40-47
+  switch (m) {
+    case 0: return 1.f;
+    case 1: return c;
+    case 2: return 2.f * c * c - 1.f;
+    case 3: return (4.f * c * c - 3.f) * c;
+    case 4: return (8.f * c * c - 8.f) * c * c + 1.f;
+    default: return ((16.f * c * c - 20.f) * c * c + 5.f) * c;
+  }
+}
+__device__ __forceinline__ float dcheb(int m, float c) {
+  switch (m) {
+    case 0: return 0.f;
+    case 1: return 1.f;
+    case 2: return 4.f * c;
+    case 3: return 12.f * c * c - 3.f;
+    case 4: return (32.f * c * c - 16.f) * c;
+    default: return (80.f * c * c - 60.f) * c * c + 5.f;
+  }
+}
+
+__global__ void __launch_bounds__(1024) row_params_kernel(MhParams p, int64_t B, const float* __restrict__ xnorm,
+                                                          const float* __restrict__ t_raw,
+                                                          const float* __restrict__ margins, float* state,
+                                                          int update_state, float* __restrict__ rowp, int64_t ldp) {
+  __shared__ double sh[32];
+  __shared__ float bc[4];
+  const float PI = 3.14159265358979323846f;
+  // ---- batch-global quantities ------------------------------------------------------------------
+  if (p.family == MH_CURRICULAR) {
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) acc += (double)fminf(fmaxf(t_raw[i], p.lo), p.hi);
+    double tot = block_sum_dd(acc, sh);
+    if (threadIdx.x == 0) {                       // criterion.py:570-573
+      float t_new = (float)(tot / (double)B) * p.momentum + (1.f - p.momentum) * state[0];
+      if (update_state) state[0] = t_new;
+      state[4] = t_new;                           // the value criterion.py:575 multiplies with
+      bc[0] = t_new;
+    }
+  } else if (p.family == MH_ADAFACE) {
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) a += (double)fminf(fmaxf(xnorm[i], 0.001f), 100.f);
+    double mean = block_sum_dd(a, sh) / (double)B;
+    double q = 0.0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+      double d = (double)fminf(fmaxf(xnorm[i], 0.001f), 100.f) - mean;
+      q += d * d;
+    }
+    double var = block_sum_dd(q, sh) / (double)(B - 1);   // torch.std is unbiased (criterion.py:880)
+    if (threadIdx.x == 0) {                               // criterion.py:881-882
+      float bm = (float)mean * p.t_alpha + (1.f - p.t_alpha) * state[1];
+      float bs = (float)sqrt(var) * p.t_alpha + (1.f - p.t_alpha) * state[2];
+      if (update_state) { state[1] = bm; state[2] = bs; }
+      bc[1] = bm; bc[2] = bs;
+    }
+  } else if (p.family == MH_MAGFACE) {
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+      float xc = fminf(fmaxf(xnorm[i], p.l_a), p.u_a);
+      a += (double)(xc / (p.u_a * p.u_a) + 1.f / xc);     // criterion.py:1237
+    }
+    double tot = block_sum_dd(a, sh);
+    if (threadIdx.x == 0) state[3] = (float)(tot / (double)B);
+  } else {
+    if (threadIdx.x == 0) state[3] = 0.f;
+  }
+  __syncthreads();
+  // ---- per-row terms ----------------------------------------------------------------------------
+  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
+    const float xn = xnorm[i];
+    const float tr = t_raw[i];
+    const float t = fminf(fmaxf(tr, p.lo), p.hi);
+    const float inside = (tr >= p.lo && tr <= p.hi) ? 1.f : 0.f;
+    float scale = p.s, thr = INFINITY, zt = 0.f, dzt = 0.f, dzt_dn = 0.f, dlg_dn = 0.f, norms = xn;
+    switch (p.family) {
+      case MH_ARCFACE: {                                  // criterion.py:281-287
+        float one_m = 1.f - t * t;
+        float sine = sqrtf(fminf(fmaxf(one_m, 1e-9f), 1.f));
+        float dsine = (one_m >= 1e-9f && one_m <= 1.f) ? -t / sine : 0.f;
+        float phi = t * p.cos_m - sine * p.sin_m;
+        float dphi = p.cos_m - dsine * p.sin_m;
+        bool take = p.easy_margin ? (t > 0.f) : (t > p.th);
+        float alt = p.easy_margin ? t : t - p.mm;
+        zt = p.s * (take ? phi : alt);
+        dzt = p.s * (take ? dphi : 1.f);
+      } break;
+      case MH_COSFACE:                                    // criterion.py:186-189
+        zt = p.s * (t - p.m);
+        dzt = p.s * inside;
+        break;
+      case MH_SPHEREFACE: {                               // criterion.py:85-105
+        float theta = acosf(t);
+        float k = floorf((float)p.sphere_m * theta / PI);
+        float sign = (fmodf(k, 2.f) == 0.f) ? 1.f : -1.f;
+        float phi = sign * cheb(p.sphere_m, t) - 2.f * k;
+        float u = (phi - t) / (1.f + p.sphere_lambda) + t;
+        float du = (sign * dcheb(p.sphere_m, t) - 1.f) / (1.f + p.sphere_lambda) + 1.f;
+        scale = xn;
+        zt = u * xn;
+        dzt = du * xn * inside;
+      } break;
+      case MH_MV_AM: {                                    // criterion.py:421-424
+        bool take = t > p.m;
+        zt = p.s * (take ? t - p.m : t);
+        dzt = p.s * inside;
+        thr = t - p.m;
+      } break;
+      case MH_MV_ARC: {                                   // criterion.py:427-430
+        float sin_t = sqrtf(1.f - t * t + 1e-9f);
+        float ctm = t * p.cos_m - sin_t * p.sin_m;
+        bool take = t > 0.f;
+        zt = p.s * (take ? ctm : t);
+        dzt = p.s * (take ? p.cos_m + t / sin_t * p.sin_m : 1.f) * inside;
+        thr = ctm;
+      } break;
+      case MH_CURRICULAR: {                               // criterion.py:555-566
+        float sin_t = sqrtf(1.f - t * t);
+        float ctm = t * p.cos_m - sin_t * p.sin_m;
+        bool take = t > p.th;
+        zt = p.s * (take ? ctm : t - p.mm);
+        dzt = p.s * (take ? p.cos_m + t / sin_t * p.sin_m : 1.f) * inside;
+        thr = ctm;
+      } break;
+      case MH_ADAFACE: {                                  // criterion.py:876-904
+        const float eps = 1e-3f;
+        float sn = fminf(fmaxf(xn, 0.001f), 100.f);
+        float ms = fminf(fmaxf((sn - bc[1]) / (bc[2] + eps) * p.h, -1.f), 1.f);
+        float th_raw = acosf(t) - p.m * ms;
+        float th_m = fminf(fmaxf(th_raw, eps), PI - eps);
+        float in2 = (th_raw >= eps && th_raw <= PI - eps) ? 1.f : 0.f;
+        zt = p.s * (cosf(th_m) - (p.m + p.m * ms));
+        dzt = p.s * sinf(th_m) / sqrtf(1.f - t * t) * in2 * inside;
+      } break;
+      case MH_ELASTIC_COS: {                              // criterion.py:1014
+        zt = p.s * (t - margins[i]);
+        dzt = p.s * inside;
+      } break;
+      case MH_ELASTIC_ARC: {                              // criterion.py:1129-1135
+        float th_raw = acosf(t) + margins[i];
+        float th_m = fminf(fmaxf(th_raw, 0.f), PI);
+        float in2 = (th_raw >= 0.f && th_raw <= PI) ? 1.f : 0.f;
+        zt = p.s * cosf(th_m);
+        dzt = p.s * sinf(th_m) / sqrtf(1.f - t * t) * in2 * inside;
+      } break;
+      case MH_MAGFACE: {                                  // criterion.py:1244-1278
+        float xc = fminf(fmaxf(xn, p.l_a), p.u_a);
+        float in_n = (xn >= p.l_a && xn <= p.u_a) ? 1.f : 0.f;
+        float ks = (p.u_margin - p.l_margin) / (p.u_a - p.l_a);
+        float a = ks * (xc - p.l_a) + p.l_margin;
+        float ca = cosf(a), sa = sinf(a);
+        float sin_t = sqrtf(1.f - t * t + 1e-9f);
+        float ctm = t * ca - sin_t * sa;
+        float dctm_dt = ca + t / sin_t * sa;
+        float dctm_da = -t * sa - sin_t * ca;
+        bool take;
+        float alt, dalt_da;
+        if (p.easy_margin) { take = t > 0.f; alt = t; dalt_da = 0.f; }
+        else { take = t > cosf(PI - a); alt = t - sinf(PI - a) * a; dalt_da = -(a * ca + sa); }
+        zt = p.s * (take ? ctm : alt);
+        dzt = p.s * (take ? dctm_dt : 1.f) * inside;
+        dzt_dn = p.s * (take ? dctm_da : dalt_da) * ks * in_n;
+        dlg_dn = (1.f / (p.u_a * p.u_a) - 1.f / (xc * xc)) / (float)B * in_n;
+        norms = xc;
+      } break;
+    }
+    rowp[MH_RP_SCALE * ldp + i] = scale;
+    rowp[MH_RP_THR * ldp + i] = thr;
+    rowp[MH_RP_ZT * ldp + i] = zt;
+    rowp[MH_RP_DZT * ldp + i] = dzt;
+    rowp[MH_RP_T * ldp + i] = t;
+    rowp[MH_RP_DZT_DN * ldp + i] = dzt_dn;
+    rowp[MH_RP_DLG_DN * ldp + i] = dlg_dn;
+    rowp[MH_RP_NORMS * ldp + i] = norms;
+  }
+  // padding rows: benign values (scale 0 -> z = 0)
+  for (int64_t i = B + threadIdx.x; i < ldp; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < MH_RP_PLANES; ++k) rowp[k * ldp + i] = (k == MH_RP_THR) ? INFINITY : 0.f;
+  }
+}
+
+extern "C" int mh_row_params(const mh_config* cfg_host, int64_t B, const float* xnorm, const float* t_raw,
+                             const float* margins, float* state, int update_state, float* rowp, int64_t ldp,
+                             void* stream) {
+  MH_CHECK_ARG(cfg_host && xnorm && t_raw && state && rowp, "null pointer");
+  MH_CHECK_ARG(B > 0 && ldp >= B, "ldp must be >= B");
+  MhParams p = mh_make_params(cfg_host);
+  MH_CHECK_ARG(p.family >= 0 && p.family <= MH_MAGFACE, "unknown family");
+  MH_CHECK_ARG((p.family != MH_ELASTIC_COS && p.family != MH_ELASTIC_ARC) || margins, "ElasticFace needs margins");
+  MH_CHECK_ARG(p.family != MH_SPHEREFACE || (p.sphere_m >= 0 && p.sphere_m <= 5), "SphereFace m must be in 0..5");
+  row_params_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p, B, xnorm, t_raw, margins, state, update_state, rowp, ldp);
+  MH_LAUNCH_OK();
+  return MH_OK;
+}

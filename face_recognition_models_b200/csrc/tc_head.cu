@@ -1,0 +1,563 @@
+// Tensor-core path of the margin head for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed
+// 128B-swizzled shared-memory stages, mbarrier pipelines, warp-specialised persistent CTAs.
+//
+// One kernel skeleton, four modes (template parameter):
+//   FWD    S = x^ w^T tile  -> clamp/margin/scale -> online max/sum-exp + rank count per row.
+//          Nothing of size B x C is written (replaces criterion.py:267-301 & siblings +
+//          nn.CrossEntropyLoss, model_utils.py:179, + accuracy, metrics.py:3-16).
+//   BWD_G  recompute the S tile -> G = (P - Y) * dz/dcos as bf16 [B_pad, C_pad].
+//   DX     dx^ partials = G . w^      (A = G K-major,  B = w^ MN-major, split over classes)
+//   DW     dw^          = G^T . x^    (A = G MN-major, B = x^ MN-major)
+//
+// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// epilogue (one TMEM lane = one accumulator row per thread).  Tile 128 x 256 x 64, 4 smem stages
+// (48 KB each), two 256-column TMEM accumulators so the epilogue of tile t overlaps the MMAs of t+1.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <map>
+#include <tuple>
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;      // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr uint32_t TMEM_COLS = 512;
+
+enum { MODE_FWD = 0, MODE_BWD_G = 1, MODE_DX = 2, MODE_DW = 3 };
+
+struct TcArgs {
+  int m_tiles, n_tiles, n_split, k_blocks_total, k_blocks_per_split;
+  int64_t total_tiles;
+  MhParams p;
+  int64_t B, C, B_pad, C_pad;
+  const float* rowp;
+  int64_t ldp;
+  const int32_t* label_local;
+  const float* state;
+  const float* lse2;
+  float* stats_tiles;
+  __nv_bfloat16* G;
+  float* out;
+  int64_t out_split_stride;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- UMMA descriptors -------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (sm_100): start addr [0,14) >>4, LBO [16,30) >>4, SBO [32,46) >>4,
+// version=1 at [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major tile [rows][64 bf16] (128 B per row, 8-row swizzle atoms of 1024 B): SBO = 1024, LBO unused.
+// One UMMA (K=16) advances the start address by 32 B inside the swizzle atom.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_base, int k16) {
+  return make_desc(tile_base + k16 * 32, 16, 1024);
+}
+// MN-major operand built from [64 K-rows][64 MN elems] boxes (8 KB each, box b covers MN 64b..64b+63):
+// LBO = 8192 (next 64-wide MN block), SBO = 1024 (next group of 8 K rows); K=16 -> +2048 B.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_base, int k16) {
+  return make_desc(tile_base + k16 * 2048, 8192, 1024);
+}
+// Instruction descriptor, kind::f16: D=F32 (bit 4), A=B=BF16 (bits 7,10), majors (15,16), N>>3 (17..22), M>>4 (24..28).
+__host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn, int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Work {
+  int m0, n0;        // output tile origin (rows of D, cols of D)
+  int kb0, kb1;      // k-block range
+  int split;         // DX split index
+  int n_tile;        // FWD: class-tile index
+};
+
+template <int MODE>
+__device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t) {
+  Work w;
+  w.split = 0;
+  w.n_tile = 0;
+  if (MODE == MODE_FWD || MODE == MODE_BWD_G) {
+    int m = (int)(t % a.m_tiles), n = (int)(t / a.m_tiles);
+    w.m0 = m * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK; w.n_tile = n;
+  } else if (MODE == MODE_DX) {
+    int per = a.m_tiles * 2;
+    int q = (int)(t % per);
+    w.split = (int)(t / per);
+    w.m0 = (q % a.m_tiles) * BM;
+    w.n0 = (q / a.m_tiles) * BN;
+    w.kb0 = w.split * a.k_blocks_per_split;
+    w.kb1 = min(a.k_blocks_total, w.kb0 + a.k_blocks_per_split);
+  } else {
+    w.m0 = (int)(t >> 1) * BM;
+    w.n0 = (int)(t & 1) * BN;
+    w.kb0 = 0; w.kb1 = a.k_blocks_total;
+  }
+  return w;
+}
+
+// ---- epilogue helpers -----------------------------------------------------------------------------
+struct RowCtx {
+  float scale, scale2, thr, t, zt2, dzt, lse2;
+  int tcol;          // tile-local target column, or -1
+  bool valid;        // row < B
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
+  uint8_t* tiles_ptr = smem_raw + (tiles_base - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + STAGES * STAGE_BYTES);
+  const uint32_t bar_full = smem_u32(bars);                         // [STAGES]
+  const uint32_t bar_empty = bar_full + 8 * STAGES;                 // [STAGES]
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES;                // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 4);          // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  constexpr bool A_MN = (MODE == MODE_DW);
+  constexpr bool B_MN = (MODE == MODE_DX || MODE == MODE_DW);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        const Work w = get_work<MODE>(a, t);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = tiles_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t fb = bar_full + 8 * stage;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, fb, kb * BK, w.m0);                       // box [64 k][128 rows]
+          } else {
+#pragma unroll
+            for (int bx = 0; bx < BM / 64; ++bx) tma_load_2d(sa + bx * 8192, &tmA, fb, w.m0 + 64 * bx, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, fb, kb * BK, w.n0);                       // box [64 k][256 rows]
+          } else {
+#pragma unroll
+            for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(sb + bx * 8192, &tmB, fb, w.n0 + 64 * bx, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BM, BN);
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
+        const Work w = get_work<MODE>(a, t);
+        const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);                       // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = tiles_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? desc_mnmajor(sa, k) : desc_kmajor(sa, k);
+            const uint64_t db = B_MN ? desc_mnmajor(sb, k) : desc_kmajor(sb, k);
+            umma_bf16(tmem_d, da, db, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);                              // frees the smem stage when MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * buf);                                  // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // =============================== epilogue ===============================
+    const int q = warp - EPI_WARP0;                 // TMEM lane quarter == warp % 4
+    const int r = q * 32 + lane;                    // row of the tile owned by this thread
+    const MhParams& p = a.p;
+    const float ha = (p.hard_kind == 2) ? a.state[4] : p.hard_a;
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
+      const Work w = get_work<MODE>(a, t);
+      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      const int64_t row = (int64_t)w.m0 + r;
+      RowCtx rc;
+      rc.valid = true; rc.tcol = -1;
+      if (MODE == MODE_FWD || MODE == MODE_BWD_G) {
+        rc.valid = row < a.B;
+        rc.scale = a.rowp[MH_RP_SCALE * a.ldp + row];
+        rc.scale2 = rc.scale * MH_LOG2E;
+        rc.thr = a.rowp[MH_RP_THR * a.ldp + row];
+        rc.t = a.rowp[MH_RP_T * a.ldp + row];
+        rc.zt2 = a.rowp[MH_RP_ZT * a.ldp + row] * MH_LOG2E;
+        rc.dzt = a.rowp[MH_RP_DZT * a.ldp + row];
+        const int32_t y = a.label_local[row];
+        if (y >= w.n0 && y < w.n0 + BN) rc.tcol = y - w.n0;
+        rc.lse2 = (MODE == MODE_BWD_G && rc.valid) ? a.lse2[row] : 0.f;
+      }
+      const int nvalid = (int)min((int64_t)BN, a.C - (int64_t)w.n0);   // valid class columns in this tile (FWD/BWD_G)
+      mbar_wait(bar_tfull + 8 * buf, bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+
+      float st_m = -INFINITY, st_l = 0.f, st_cnt = 0.f, st_ez = 0.f;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = c * 32;
+        if (MODE == MODE_FWD) {
+          const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid);
+          float z2[32];
+          float zmax = -INFINITY;
+          if (!slow) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              ElemOut e = mh_elem(__uint_as_float(v[k]), p.lo, p.hi, p.hard_kind, rc.thr, ha, p.hard_b);
+              z2[k] = rc.scale2 * e.u;
+              st_cnt += (e.c > rc.t) ? 1.f : 0.f;
+              zmax = fmaxf(zmax, z2[k]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              ElemOut e = mh_elem(__uint_as_float(v[k]), p.lo, p.hi, p.hard_kind, rc.thr, ha, p.hard_b);
+              float z = rc.scale2 * e.u;
+              const int col = col0 + k;
+              if (col == rc.tcol) z = rc.zt2;
+              else if (col < nvalid) st_cnt += (e.c > rc.t) ? 1.f : 0.f;
+              if (col >= nvalid) z = -INFINITY;
+              z2[k] = z;
+              zmax = fmaxf(zmax, z);
+            }
+          }
+          if (zmax > st_m) {
+            const float rs = ex2(st_m - zmax);      // st_m = -inf -> 0
+            st_l *= rs; st_ez *= rs; st_m = zmax;
+          }
+          if (st_m > -INFINITY) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float e = ex2(z2[k] - st_m);
+              st_l += e;
+              if (p.scale_is_norm) st_ez = fmaf(e, fmaxf(z2[k], -1e30f), st_ez);   // masked cols: 0 * -inf guard
+            }
+          }
+        } else if (MODE == MODE_BWD_G) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            float g2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              ElemOut e = mh_elem(__uint_as_float(v[k + h]), p.lo, p.hi, p.hard_kind, rc.thr, ha, p.hard_b);
+              float z = rc.scale2 * e.u, dzdc = rc.scale * e.du, yv = 0.f;
+              const int col = col0 + k + h;
+              if (col == rc.tcol) { z = rc.zt2; dzdc = rc.dzt; yv = 1.f; }
+              float g = (ex2(z - rc.lse2) - yv) * dzdc;
+              if (col >= nvalid || !rc.valid) g = 0.f;
+              g2[h] = g;
+            }
+            __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
+            pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(a.G + row * a.C_pad + w.n0 + col0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        } else {
+          float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            reinterpret_cast<uint4*>(dst)[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+      }
+      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (MODE == MODE_FWD) {
+        float* sp = a.stats_tiles + (int64_t)w.n_tile * MH_ST_PLANES * a.B_pad;
+        sp[MH_ST_M * a.B_pad + row] = st_m;
+        sp[MH_ST_L * a.B_pad + row] = st_l;
+        sp[MH_ST_CNT * a.B_pad + row] = st_cnt;
+        // EZ accumulates e * z2 = e * u * scale2 ; store sum e*u
+        sp[MH_ST_EZ * a.B_pad + row] = (p.scale_is_norm && rc.scale2 != 0.f) ? st_ez / rc.scale2 : 0.f;
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side: tensor maps ------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+// 2-D row-major bf16 matrix [rows][cols]; box = [box_rows][64 cols] with the 128B swizzle.
+int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { mh_set_error("cuTensorMapEncodeTiled entry point not found"); return MH_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mh_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return MH_ERR_CUDA; }
+  return MH_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int MODE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = (int)std::min<int64_t>(args.total_tiles, num_sms());
+  tc_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, args);
+  MH_LAUNCH_OK();
+  return MH_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { return (C_pad + BN - 1) / BN; }
+
+static int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
+  MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % BM == 0, "B_pad must be a multiple of 128");
+  MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % BN == 0, "C_pad must be a multiple of 256 for the tensor-core path");
+  MH_CHECK_ARG(C_pad < (1ll << 31) && B_pad < (1ll << 31), "dimension too large");
+  return MH_OK;
+}
+
+extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
+                             const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
+                             const int32_t* label_local, const float* state, float* stats_tiles, void* stream) {
+  MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && stats_tiles, "null pointer");
+  if (int e = check_common(B, B_pad, C, C_pad)) return e;
+  MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&ta, x_hat_bf16, B_pad, MH_D, BM)) return e;
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN)) return e;
+  TcArgs a{};
+  a.m_tiles = (int)(B_pad / BM); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
+  a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
+  a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
+  a.p = mh_make_params(cfg_host);
+  a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
+  a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.stats_tiles = stats_tiles;
+  return launch<MODE_FWD>(ta, tb, a, (cudaStream_t)stream);
+}
+
+extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
+                                const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
+                                const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
+                                void* stream) {
+  MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && lse2 && G_bf16, "null pointer");
+  if (int e = check_common(B, B_pad, C, C_pad)) return e;
+  MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&ta, x_hat_bf16, B_pad, MH_D, BM)) return e;
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN)) return e;
+  TcArgs a{};
+  a.m_tiles = (int)(B_pad / BM); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
+  a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
+  a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
+  a.p = mh_make_params(cfg_host);
+  a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
+  a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.lse2 = lse2;
+  a.G = (__nv_bfloat16*)G_bf16;
+  return launch<MODE_BWD_G>(ta, tb, a, (cudaStream_t)stream);
+}
+
+extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
+                                 int* n_split_host, void* stream) {
+  MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
+  const int m_tiles = (int)(B_pad / BM);
+  const int kb_total = (int)(C_pad / BK);
+  int n_split = std::max(1, num_sms() / (m_tiles * 2));
+  n_split = std::min(n_split, kb_total);
+  int per = (kb_total + n_split - 1) / n_split;
+  n_split = (kb_total + per - 1) / per;                 // no empty splits
+  if (n_split_host) *n_split_host = n_split;
+  if (!out) return MH_OK;
+  MH_CHECK_ARG(G_bf16 && w_hat_bf16, "null pointer");
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, BM)) return e;          // A = G, K-major (K = class)
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, 64)) return e;       // B = w^, MN-major boxes [64 k][64 d]
+  TcArgs a{};
+  a.m_tiles = m_tiles; a.n_tiles = 2; a.n_split = n_split;
+  a.k_blocks_total = kb_total; a.k_blocks_per_split = per;
+  a.total_tiles = (int64_t)m_tiles * 2 * n_split;
+  a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
+  a.out = out; a.out_split_stride = B_pad * MH_D;
+  return launch<MODE_DX>(ta, tb, a, (cudaStream_t)stream);
+}
+
+extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
+                                 float* dw_hat, void* stream) {
+  MH_CHECK_ARG(G_bf16 && x_hat_bf16 && dw_hat, "null pointer");
+  MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, 64)) return e;          // A = G^T, MN-major boxes [64 rows][64 cls]
+  if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;       // B = x^,  MN-major boxes [64 rows][64 d]
+  TcArgs a{};
+  a.m_tiles = (int)(C_pad / BM); a.n_tiles = 2; a.n_split = 1;
+  a.k_blocks_total = (int)(B_pad / BK); a.k_blocks_per_split = a.k_blocks_total;
+  a.total_tiles = (int64_t)a.m_tiles * 2;
+  a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
+  a.out = dw_hat; a.out_split_stride = 0;
+  return launch<MODE_DW>(ta, tb, a, (cudaStream_t)stream);
+}

@@ -1,0 +1,338 @@
+"""Host-side engine of the margin head: workspaces, kernel sequencing, autograd glue.
+
+Two execution paths, both CUDA only (there is no CPU / PyTorch fallback):
+
+* ``tc``    - bf16 tensor-core path (tcgen05 + TMEM + TMA).  Forward never materialises B x C;
+              backward recomputes the logit tiles and keeps only G = (P-Y) dz/dcos in bf16.
+* ``exact`` - fp32 SIMT path that materialises the cosine matrix (small C: fp32-tolerance mode,
+              and the compat mode returning the reference's 4-tuple).
+
+The sequence mirrors the reference forward (criterion.py, any head) + ``nn.CrossEntropyLoss`` +
+``accuracy`` of model_utils.py:176-182, and autograd's backward of all of it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _round_up(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+_DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}
+
+
+def sphere_lambda(it: int) -> float:
+    """SphereFace annealing, criterion.py:60 (base 1000, gamma 0.12, power 1, LambdaMin 5)."""
+    return max(5.0, 1000.0 * (1 + 0.12 * it) ** (-1))
+
+
+@dataclass
+class ShardInfo:
+    """Class-dimension sharding (Partial-FC style): this rank owns [c_offset, c_offset + C_local)."""
+    group: object = None
+    rank: int = 0
+    world: int = 1
+    c_offset: int = 0
+
+
+class HeadEngine:
+    """Owns the device workspaces of one head and runs the kernel pipeline through the C ABI."""
+
+    def __init__(self, family: str, layout: str, num_classes_local: int, cfg_kwargs: Dict,
+                 mode: str = "tc", shard: Optional[ShardInfo] = None):
+        assert family in L.FAMILY, family
+        assert layout in ("CD", "DC")
+        assert mode in ("tc", "exact")
+        self.family = family
+        self.layout = L.LAYOUT_CD if layout == "CD" else L.LAYOUT_DC
+        self.C = int(num_classes_local)
+        self.mode = mode
+        self.shard = shard or ShardInfo()
+        self.cfg = L.MhConfig()
+        self.cfg.family = L.FAMILY[family]
+        self.cfg.s = 64.0
+        for k, v in cfg_kwargs.items():
+            setattr(self.cfg, k, v)
+        self._ws: Dict[str, torch.Tensor] = {}
+        self._gen = 0
+
+    # -- workspace ------------------------------------------------------------------------------
+    def _buf(self, name: str, shape, dtype, device, zero: bool = False) -> torch.Tensor:
+        key = name
+        t = self._ws.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            self._ws[key] = t
+        return t
+
+    def release_workspaces(self):
+        self._ws.clear()
+
+    # -- forward ----------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, state: torch.Tensor,
+                margins: Optional[torch.Tensor], update_state: bool = True, want_dense: bool = False):
+        """Runs prologues + fused forward.  x is the (already gathered) global batch [B, 512].
+
+        Returns a context dict with every tensor the backward needs plus the user-visible outputs.
+        """
+        lib = L.load()
+        if not x.is_cuda:
+            raise L.MarginHeadError("margin head inputs must be CUDA tensors (no CPU fallback)")
+        L.check(lib.mh_device_check(), "mh_device_check")
+        assert x.dim() == 2 and x.shape[1] == L.D, "embedding dimension must be 512"
+        assert x.dtype in _DT, x.dtype
+        assert W.dtype == torch.float32 and W.is_contiguous()
+        x = x.contiguous()
+        labels = labels.contiguous().to(torch.int64)
+        dev = x.device
+        B = x.shape[0]
+        Cn = self.C
+        B_pad = _round_up(B, L.TILE)
+        C_pad = _round_up(Cn, L.NTILE)
+        ld = W.shape[1]
+        if self.layout == L.LAYOUT_CD:
+            assert tuple(W.shape) == (Cn, L.D), (W.shape, Cn)
+        else:
+            assert tuple(W.shape) == (L.D, Cn), (W.shape, Cn)
+        st = _stream()
+        exact = self.mode == "exact" or want_dense
+        self._gen += 1
+
+        w_hat = self._buf("w_hat", (C_pad, L.D), torch.bfloat16, dev)
+        inv_norm = self._buf("inv_norm", (Cn,), torch.float32, dev)
+        w_hat32 = self._buf("w_hat32", (Cn, L.D), torch.float32, dev) if exact else None
+        L.call("mh_prologue_w", _ptr(W), self.layout, Cn, ld, _ptr(w_hat), C_pad, _ptr(w_hat32), _ptr(inv_norm), st)
+
+        x_hat = self._buf("x_hat", (B_pad, L.D), torch.bfloat16, dev)
+        x_hat32 = self._buf("x_hat32", (B, L.D), torch.float32, dev)
+        xnorm = self._buf("xnorm", (B,), torch.float32, dev)
+        t_raw = self._buf("t_raw", (B,), torch.float32, dev)
+        label_local = self._buf("label_local", (B_pad,), torch.int32, dev)
+        L.call("mh_prologue_x", _ptr(x), _DT[x.dtype], B, B_pad, _ptr(labels), _ptr(W), self.layout, Cn, ld,
+               self.shard.c_offset, _ptr(inv_norm), _ptr(x_hat), _ptr(x_hat32), _ptr(xnorm), _ptr(t_raw),
+               _ptr(label_local), st)
+        if self.shard.world > 1:
+            # every rank needs every row's target cosine (thresholds, EMA); only the owner computed it
+            torch.distributed.all_reduce(t_raw, group=self.shard.group)
+
+        if self.family in ("elastic_cos", "elastic_arc"):
+            assert margins is not None and margins.numel() == B
+            margins = margins.to(device=dev, dtype=torch.float32).contiguous()
+            if self.cfg.plus:
+                # criterion.py:1007-1012 exactly as written: sorted margins indexed by the permutation
+                lo, hi = -1 + 1e-7, 1 - 1e-7
+                rank = torch.sort(t_raw.clamp(lo, hi), descending=True)[1]
+                margins = torch.sort(margins)[0][rank].contiguous()
+        else:
+            margins = None
+
+        rowp = self._buf("rowp", (L.RP_PLANES, B_pad), torch.float32, dev)
+        L.call("mh_row_params", C.byref(self.cfg), B, _ptr(xnorm), _ptr(t_raw), _ptr(margins), _ptr(state),
+               1 if update_state else 0, _ptr(rowp), B_pad, st)
+
+        stats = self._buf("stats", (L.ST_PLANES, B_pad), torch.float32, dev)
+        S = pre = logits = None
+        if exact:
+            S = self._buf("S", (B, Cn), torch.float32, dev)
+            # S = x_hat32 [B,512] . w_hat32^T  (w_hat32 is [C,512]: B operand strides (1, 512))
+            L.call("mh_sgemm_strided", B, Cn, L.D, _ptr(x_hat32), L.D, 1, _ptr(w_hat32), 1, L.D, _ptr(S), Cn, st)
+            if want_dense:
+                pre = torch.empty((B, Cn), dtype=torch.float32, device=dev)
+                logits = torch.empty((B, Cn), dtype=torch.float32, device=dev)
+            L.call("mh_dense_forward", C.byref(self.cfg), _ptr(S), Cn, B, B_pad, Cn, _ptr(rowp), B_pad,
+                   _ptr(label_local), _ptr(state), _ptr(stats), _ptr(pre), _ptr(logits), st)
+        else:
+            n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
+            stats_tiles = self._buf("stats_tiles", (n_tiles, L.ST_PLANES, B_pad), torch.float32, dev)
+            scratch = self._buf("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev)
+            L.call("mh_tc_forward", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_hat), Cn, C_pad, _ptr(rowp), B_pad,
+                   _ptr(label_local), _ptr(state), _ptr(stats_tiles), st)
+            L.call("mh_merge_stats", _ptr(stats_tiles), n_tiles, B, B_pad, _ptr(scratch), _ptr(stats), st)
+
+        if self.shard.world > 1:
+            all_stats = self._buf("all_stats", (self.shard.world, L.ST_PLANES, B_pad), torch.float32, dev)
+            torch.distributed.all_gather_into_tensor(all_stats, stats, group=self.shard.group)
+            scratch = self._buf("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev)
+            L.call("mh_merge_stats", _ptr(all_stats), self.shard.world, B, B_pad, _ptr(scratch), _ptr(stats), st)
+
+        rowout = self._buf("rowout", (L.RO_PLANES, B_pad), torch.float32, dev)
+        scalars = torch.empty(3, dtype=torch.float32, device=dev)
+        L.call("mh_finalize_rows", _ptr(stats), B_pad, _ptr(rowp), B_pad, B, B, 1 if self.family == "sphereface" else 0,
+               _ptr(rowout), B_pad, _ptr(scalars), st)
+        return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=w_hat, w_hat32=w_hat32, inv_norm=inv_norm,
+                    x_hat=x_hat, x_hat32=x_hat32, xnorm=xnorm, label_local=label_local, rowp=rowp, rowout=rowout,
+                    scalars=scalars, S=S, pre=pre, logits=logits, exact=exact, gen=self._gen, state=state,
+                    W_shape=tuple(W.shape), ld=ld)
+
+    # -- backward of the fused loss ------------------------------------------------------------------
+    def backward(self, ctx: Dict, g_loss: torch.Tensor, g_lossg: Optional[torch.Tensor],
+                 need_dx: bool = True, need_dw: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Returns (dxhat_partials_or_dx, dW).  For world == 1 the first element is dx [B,512] in x's dtype."""
+        if ctx["gen"] != self._gen:
+            raise L.MarginHeadError("margin head workspaces were overwritten by a later forward; "
+                                    "run backward before the next forward of the same head")
+        dev = ctx["x_hat"].device
+        B, B_pad, C_pad, Cn = ctx["B"], ctx["B_pad"], ctx["C_pad"], self.C
+        st = _stream()
+        gscal = torch.zeros(2, dtype=torch.float32, device=dev)
+        gscal[0] = g_loss.to(torch.float32) / B
+        if g_lossg is not None:
+            gscal[1] = g_lossg.to(torch.float32)
+        rowp, rowout, state = ctx["rowp"], ctx["rowout"], ctx["state"]
+        lse2 = rowout[L.RO["LSE2"]]
+        if ctx["exact"]:
+            S = ctx["S"]
+            L.call("mh_dense_backward_dc", C.byref(self.cfg), _ptr(S), Cn, B, Cn, _ptr(rowp), B_pad,
+                   _ptr(ctx["label_local"]), _ptr(state), _ptr(lse2), _ptr(None), _ptr(None), _ptr(None), st)
+            return self._exact_grads(ctx, S, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]], need_dx, need_dw)
+        G = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
+        L.call("mh_tc_backward_g", C.byref(self.cfg), _ptr(ctx["x_hat"]), B, B_pad, _ptr(ctx["w_hat"]), Cn, C_pad,
+               _ptr(rowp), B_pad, _ptr(ctx["label_local"]), _ptr(state), _ptr(lse2), _ptr(G), st)
+        dx = dW = None
+        if need_dx:
+            ns = C.c_int(0)
+            L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(ctx["w_hat"]), _ptr(None), C.byref(ns), st)
+            n_split = ns.value
+            part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
+            L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(ctx["w_hat"]), _ptr(part), C.byref(ns), st)
+            dx = self._finish_dx(ctx, part, n_split, B_pad * L.D, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
+        if need_dw:
+            dw_hat = self._buf("dw_hat", (C_pad, L.D), torch.float32, dev)
+            L.call("mh_tc_backward_dw", _ptr(G), B_pad, C_pad, _ptr(ctx["x_hat"]), _ptr(dw_hat), st)
+            dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
+            L.call("mh_norm_backward_w", _ptr(dw_hat), _ptr(ctx["w_hat"]), _ptr(None), _ptr(ctx["inv_norm"]), _ptr(gscal),
+                   Cn, self.layout, _ptr(dW), ctx["ld"], st)
+        return dx, dW
+
+    def _finish_dx(self, ctx, part, n_split, split_stride, gscal, aux0, aux1):
+        """Sum split partials (+ cross-rank reduce-scatter when sharded) and apply normalise-backward."""
+        B = ctx["B"]
+        dev = part.device
+        st = _stream()
+        if self.shard.world > 1:
+            R = self.shard.world
+            assert B % R == 0
+            Bl = B // R
+            full = part[:, :B].sum(dim=0) if n_split > 1 else part[0, :B]
+            mine = torch.empty((Bl, L.D), dtype=torch.float32, device=dev)
+            torch.distributed.reduce_scatter_tensor(mine, full.contiguous(), group=self.shard.group)
+            r0 = self.shard.rank * Bl
+            dx = torch.empty((Bl, L.D), dtype=ctx["x_dtype"], device=dev)
+            rowp_off = ctx["rowp"][:, r0:]
+            # rowp planes stay at pitch B_pad; offsetting the base pointer by r0 rows keeps the pitch valid
+            L.call("mh_norm_backward_x", _ptr(mine), 1, 0, _ptr(ctx["x_hat32"][r0:]), _ptr(ctx["xnorm"][r0:]),
+                   C.c_void_p(rowp_off.data_ptr()), ctx["B_pad"], C.c_void_p(aux0[r0:].data_ptr()),
+                   C.c_void_p(aux1[r0:].data_ptr()), _ptr(gscal), Bl, _ptr(dx), _DT[ctx["x_dtype"]], st)
+            return dx
+        dx = torch.empty((B, L.D), dtype=ctx["x_dtype"], device=dev)
+        L.call("mh_norm_backward_x", _ptr(part), n_split, split_stride, _ptr(ctx["x_hat32"]), _ptr(ctx["xnorm"]),
+               _ptr(ctx["rowp"]), ctx["B_pad"], _ptr(aux0), _ptr(aux1), _ptr(gscal), B, _ptr(dx), _DT[ctx["x_dtype"]], st)
+        return dx
+
+    def _exact_grads(self, ctx, dc, gscal, aux0, aux1, need_dx, need_dw):
+        """dx^ = dc . w^ ; dw^ = dc^T . x^ with the fp32 SIMT GEMM, then the normalise-backward kernels."""
+        dev = dc.device
+        B, Cn = ctx["B"], self.C
+        st = _stream()
+        dx = dW = None
+        if need_dx:
+            dxh = self._buf("dxhat_exact", (1, B, L.D), torch.float32, dev)
+            L.call("mh_sgemm_strided", B, L.D, Cn, _ptr(dc), Cn, 1, _ptr(ctx["w_hat32"]), L.D, 1, _ptr(dxh), L.D, st)
+            dx = self._finish_dx(ctx, dxh, 1, B * L.D, gscal, aux0, aux1)
+        if need_dw:
+            dwh = self._buf("dw_hat_exact", (Cn, L.D), torch.float32, dev)
+            # dw^ [C,512] = dc^T [C,B] . x^ [B,512] : A strides (1, C)
+            L.call("mh_sgemm_strided", Cn, L.D, B, _ptr(dc), 1, Cn, _ptr(ctx["x_hat32"]), L.D, 1, _ptr(dwh), L.D, st)
+            dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
+            L.call("mh_norm_backward_w", _ptr(dwh), _ptr(None), _ptr(ctx["w_hat32"]), _ptr(ctx["inv_norm"]), _ptr(gscal),
+                   Cn, self.layout, _ptr(dW), ctx["ld"], st)
+        return dx, dW
+
+    # -- backward of the compat (materialised logits) outputs ---------------------------------------
+    def backward_dense(self, ctx: Dict, dlogits: Optional[torch.Tensor], dpre: Optional[torch.Tensor],
+                       g_lossg: Optional[torch.Tensor], need_dx=True, need_dw=True):
+        if ctx["gen"] != self._gen:
+            raise L.MarginHeadError("margin head workspaces were overwritten by a later forward")
+        dev = ctx["x_hat"].device
+        B, B_pad, Cn = ctx["B"], ctx["B_pad"], self.C
+        st = _stream()
+        if dlogits is None:
+            dlogits = torch.zeros((B, Cn), dtype=torch.float32, device=dev)
+        dlogits = dlogits.to(torch.float32).contiguous()
+        dpre = dpre.to(torch.float32).contiguous() if dpre is not None else None
+        rowaux = torch.zeros((2, B), dtype=torch.float32, device=dev)
+        S = ctx["S"]
+        L.call("mh_dense_backward_dc", C.byref(self.cfg), _ptr(S), Cn, B, Cn, _ptr(ctx["rowp"]), B_pad,
+               _ptr(ctx["label_local"]), _ptr(ctx["state"]), _ptr(None), _ptr(dlogits), _ptr(dpre), _ptr(rowaux), st)
+        gscal = torch.zeros(2, dtype=torch.float32, device=dev)
+        gscal[0] = 1.0
+        if g_lossg is not None:
+            gscal[1] = g_lossg.to(torch.float32)
+        return self._exact_grads(ctx, S, gscal, rowaux[0], rowaux[1], need_dx, need_dw)
+
+
+class FusedMarginLossFn(torch.autograd.Function):
+    """loss_id, loss_g, acc1, acc5, norms = f(x, W, labels).  Only loss_id / loss_g are differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, W, labels, engine: HeadEngine, state, margins, update_state):
+        c = engine.forward(x, W, labels, state, margins, update_state=update_state)
+        ctx.engine = engine
+        ctx.c = c
+        ctx.x_dtype = x.dtype
+        sc = c["scalars"]
+        loss = sc[0].clone()
+        loss_g = state[3].clone()
+        norms = c["rowp"][L.RP["NORMS"], :c["B"]].clone().unsqueeze(1)
+        ctx.mark_non_differentiable(norms)
+        acc1, acc5 = sc[1].clone(), sc[2].clone()
+        ctx.mark_non_differentiable(acc1, acc5)
+        return loss, loss_g, acc1, acc5, norms
+
+    @staticmethod
+    def backward(ctx, g_loss, g_lossg, _ga1, _ga5, _gn):
+        eng = ctx.engine
+        if g_loss is None:
+            g_loss = torch.zeros((), device=ctx.c["x_hat"].device)
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx, dW = eng.backward(ctx.c, g_loss, g_lossg, need_dx, need_dw)
+        return dx, dW, None, None, None, None, None
+
+
+class DenseMarginLogitsFn(torch.autograd.Function):
+    """Compat mode: materialise the reference's ``[pre_margin_logits, logits]`` (criterion.py:301 etc.)."""
+
+    @staticmethod
+    def forward(ctx, x, W, labels, engine: HeadEngine, state, margins, update_state):
+        c = engine.forward(x, W, labels, state, margins, update_state=update_state, want_dense=True)
+        ctx.engine = engine
+        ctx.c = c
+        norms = c["rowp"][L.RP["NORMS"], :c["B"]].clone().unsqueeze(1)
+        loss_g = state[3].clone()
+        ctx.mark_non_differentiable(norms)
+        return c["pre"], c["logits"], norms, loss_g
+
+    @staticmethod
+    def backward(ctx, dpre, dlogits, _gn, g_lossg):
+        eng = ctx.engine
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if dpre is not None and not bool(torch.count_nonzero(dpre)):
+            dpre = None
+        dx, dW = eng.backward_dense(ctx.c, dlogits, dpre, g_lossg, need_dx, need_dw)
+        return dx, dW, None, None, None, None, None

@@ -1,0 +1,308 @@
+"""Drop-in nn.Modules for the reference's margin heads (main_code/utils/criterion.py).
+
+Each class has the reference's constructor signature and defaults, the same parameter / buffer
+names, shapes, layouts and initialisation (so ``state_dict``s interchange and a wrapper such as
+``ArcFaceNet`` can assign ``self.arcface = ArcFace(...)`` unchanged), and two call styles:
+
+* ``head(feats, labels)``            -> ``([pre_margin_logits, logits], norms, loss_g, one_hot)``
+  the reference's 4-tuple (compat mode, materialises B x C in fp32 - small class counts only;
+  this is what the unchanged ``train_model`` consumes, model_utils.py:177-182).
+* ``head.fused_loss(feats, labels)`` -> ``FusedOutput(loss, loss_g, acc1, acc5, norms)``
+  the fused path: cross-entropy (mean), top-1/top-5 and the gradients come from the sm_100a
+  kernels and nothing of size B x C is materialised in the forward.
+
+All compute goes through libmargin_head.so; there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .functional import DenseMarginLogitsFn, FusedMarginLossFn, HeadEngine, ShardInfo, sphere_lambda
+
+
+class FusedOutput(NamedTuple):
+    loss: torch.Tensor       # mean cross-entropy over the batch (nn.CrossEntropyLoss(), model_utils.py:556)
+    loss_g: torch.Tensor     # MagFace regulariser (0 for the other heads); caller adds lambda_g * loss_g
+    acc1: torch.Tensor       # top-1 accuracy in percent on the pre-margin logits (metrics.py:3-16)
+    acc5: torch.Tensor
+    norms: torch.Tensor      # [B, 1], as returned by the reference head
+
+
+class _MarginHeadBase(nn.Module):
+    family = ""
+    layout = "CD"
+    param_name = "weight"
+
+    def _init_engine(self, num_classes: int, mode: str = "tc", **cfg):
+        self._engine = HeadEngine(self.family, self.layout, num_classes, cfg, mode=mode)
+        self._num_classes = num_classes
+        # device-side state vector shared with the kernels (see MH_STATE_FLOATS in margin_head.h)
+        self.register_buffer("_mh_state", torch.zeros(L.STATE_FLOATS), persistent=False)
+        self._margins_override: Optional[torch.Tensor] = None
+
+    # precision / path selection: "tc" (bf16 tensor cores) or "exact" (fp32 SIMT, small C)
+    @property
+    def mode(self) -> str:
+        return self._engine.mode
+
+    @mode.setter
+    def mode(self, v: str):
+        assert v in ("tc", "exact")
+        self._engine.mode = v
+
+    def _param(self) -> torch.Tensor:
+        return getattr(self, self.param_name)
+
+    # hooks for heads with state ------------------------------------------------------------------
+    def _push_state(self):
+        pass
+
+    def _pull_state(self):
+        pass
+
+    def _pre_forward(self, feats):
+        pass
+
+    def _sample_margins(self, feats, labels):
+        return None
+
+    # ------------------------------------------------------------------------------------------------
+    def _check(self, feats, labels):
+        if labels is None:
+            raise ValueError("labels are required in training mode")
+        if feats.dim() != 2 or feats.shape[1] != L.D:
+            raise ValueError(f"expected feats of shape [B, {L.D}], got {tuple(feats.shape)}")
+        if labels.shape[0] != feats.shape[0]:
+            raise ValueError("feats / labels batch mismatch")
+
+    def fused_loss(self, feats: torch.Tensor, labels: torch.Tensor) -> FusedOutput:
+        self._check(feats, labels)
+        self._pre_forward(feats)
+        margins = self._sample_margins(feats, labels)
+        self._push_state()
+        out = FusedMarginLossFn.apply(feats, self._param(), labels, self._engine, self._mh_state, margins,
+                                      self.training or True)
+        self._pull_state()
+        return FusedOutput(*out)
+
+    def forward(self, feats: torch.Tensor, labels: torch.Tensor):
+        self._check(feats, labels)
+        self._pre_forward(feats)
+        margins = self._sample_margins(feats, labels)
+        self._push_state()
+        pre, logits, norms, loss_g = DenseMarginLogitsFn.apply(feats, self._param(), labels, self._engine,
+                                                               self._mh_state, margins, True)
+        self._pull_state()
+        one_hot = torch.zeros_like(logits)
+        one_hot.scatter_(1, labels.view(-1, 1), 1.0)
+        if self.family != "magface":
+            loss_g = 0                      # the reference returns the int 0 (criterion.py:107,195,299,449,587,907,1021)
+        return [pre, logits], norms, loss_g, one_hot
+
+    def get_proxy(self, labels: torch.Tensor) -> torch.Tensor:
+        """Raw class centres for the given labels, [D, N] (CosFace.get_proxy, criterion.py:157-159)."""
+        W = self._param()
+        return (W[labels].t() if self.layout == "CD" else W[:, labels]).clone().detach()
+
+
+def _insightface_init(p: torch.Tensor):
+    # criterion.py:152,367,833,1218
+    p.data.uniform_(-1, 1).renorm_(2, 1, 1e-5).mul_(1e5)
+
+
+class SphereFace(_MarginHeadBase):
+    """criterion.py:12-107."""
+    family, layout, param_name = "sphereface", "CD", "weight"
+
+    def __init__(self, in_features: int, out_features: int, device_id=None, m: int = 4):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.in_features, self.out_features, self.m, self.device_id = in_features, out_features, m, device_id
+        self.base, self.gamma, self.power, self.LambdaMin, self.iter = 1000.0, 0.12, 1, 5.0, 0
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        nn.init.xavier_uniform_(self.weight)
+        self._init_engine(out_features, sphere_m=int(m))
+
+    def _pre_forward(self, feats):
+        self.iter += 1                                                   # criterion.py:58-60
+        self.lamb = max(self.LambdaMin, self.base * (1 + self.gamma * self.iter) ** (-self.power))
+        self._engine.cfg.sphere_lambda = self.lamb
+
+
+class CosFace(_MarginHeadBase):
+    """criterion.py:137-197."""
+    family, layout, param_name = "cosface", "DC", "kernel"
+
+    def __init__(self, embedding_size=512, classnum=51332, s: float = 64.0, m: float = 0.4):
+        super().__init__()
+        self.classnum, self.s, self.m, self.eps = classnum, s, m, 1e-4
+        self.kernel = nn.Parameter(torch.empty(embedding_size, classnum))
+        _insightface_init(self.kernel)
+        self._init_engine(classnum, s=s, m=m)
+
+
+class ArcFace(_MarginHeadBase):
+    """criterion.py:232-301."""
+    family, layout, param_name = "arcface", "CD", "weight"
+
+    def __init__(self, embed_size, num_classes, device_id=None, s=64.0, m=0.50, easy_margin=True):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.in_features, self.out_features, self.device_id = embed_size, num_classes, device_id
+        self.s, self.m, self.easy_margin = s, m, easy_margin
+        self.weight = nn.Parameter(torch.empty(num_classes, embed_size))
+        nn.init.xavier_uniform_(self.weight)
+        self.cos_m, self.sin_m = math.cos(m), math.sin(m)
+        self.th, self.mm = math.cos(math.pi - m), math.sin(math.pi - m) * m
+        self._init_engine(num_classes, s=s, m=m, easy_margin=int(bool(easy_margin)))
+
+
+class MV_Softmax(_MarginHeadBase):
+    """criterion.py:327-461."""
+    layout, param_name = "CD", "weight"
+
+    def __init__(self, feat_dim: int, num_class: int, margin: float = 0.35, mv_weight: float = 1.12,
+                 s: float = 32.0, margin_type: str = "arc", device_id=None):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.feat_dim, self.num_class, self.margin, self.mv_weight, self.s = feat_dim, num_class, margin, mv_weight, s
+        self.margin_type = margin_type.lower()
+        self.device_id = device_id
+        assert self.margin_type in ("am", "arc"), "margin_type must be 'am' or 'arc'"
+        self.weight = nn.Parameter(torch.empty(num_class, feat_dim))
+        _insightface_init(self.weight)
+        if self.margin_type == "arc":
+            self.cos_m, self.sin_m = math.cos(margin), math.sin(margin)
+            self.th, self.mm = math.cos(math.pi - margin), math.sin(margin) * margin
+        self.family = "mv_am" if self.margin_type == "am" else "mv_arc"
+        self._init_engine(num_class, s=s, m=margin, mv_weight=mv_weight)
+
+    def _pre_forward(self, feats):
+        # evaluate_models.py:50,53 flips margin_type after construction; honour it
+        fam = "mv_am" if self.margin_type == "am" else "mv_arc"
+        if fam != self._engine.family:
+            self.family = fam
+            self._engine.family = fam
+            self._engine.cfg.family = L.FAMILY[fam]
+
+
+class CurricularFace(_MarginHeadBase):
+    """criterion.py:491-587."""
+    family, layout, param_name = "curricularface", "DC", "kernel"
+
+    def __init__(self, feat_dim: int, num_class: int, m: float = 0.5, s: float = 64.0, momentum: float = 0.01):
+        super().__init__()
+        self.m, self.s, self.momentum = m, s, momentum
+        self.cos_m, self.sin_m = math.cos(m), math.sin(m)
+        self.threshold, self.mm = math.cos(math.pi - m), math.sin(math.pi - m) * m
+        self.kernel = nn.Parameter(torch.empty(feat_dim, num_class))
+        nn.init.normal_(self.kernel, std=0.01)
+        self.register_buffer("t", torch.zeros(1))
+        self._init_engine(num_class, s=s, m=m, momentum=momentum)
+
+    def _push_state(self):
+        self._mh_state[0:1].copy_(self.t.to(torch.float32))
+
+    def _pull_state(self):
+        self.t = self._mh_state[0:1].clone()
+
+
+class AdaFace(_MarginHeadBase):
+    """criterion.py:795-918."""
+    family, layout, param_name = "adaface", "DC", "kernel"
+
+    def __init__(self, feat_dim: int, num_class: int, m: float = 0.4, h: float = 0.333, s: float = 64.0,
+                 t_alpha: float = 1.0, device_id=None):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.feat_dim, self.num_class, self.m, self.h, self.s, self.t_alpha = feat_dim, num_class, m, h, s, t_alpha
+        self.device_id, self.eps = device_id, 1e-3
+        self.kernel = nn.Parameter(torch.empty(feat_dim, num_class))
+        _insightface_init(self.kernel)
+        self.register_buffer("t", torch.zeros(1))
+        self.register_buffer("batch_mean", torch.ones(1) * 20)
+        self.register_buffer("batch_std", torch.ones(1) * 100)
+        self._init_engine(num_class, s=s, m=m, h=h, t_alpha=t_alpha)
+
+    def _push_state(self):
+        self._mh_state[1:2].copy_(self.batch_mean.to(torch.float32))
+        self._mh_state[2:3].copy_(self.batch_std.to(torch.float32))
+
+    def _pull_state(self):
+        self.batch_mean = self._mh_state[1:2].clone()
+        self.batch_std = self._mh_state[2:3].clone()
+
+
+class _ElasticBase(_MarginHeadBase):
+    layout, param_name = "DC", "kernel"
+
+    def __init__(self, feat_dim: int, num_class: int, s: float, m: float, std: float, plus: bool, device_id):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.feat_dim, self.num_class, self.s, self.m, self.std, self.plus = feat_dim, num_class, s, m, std, plus
+        self.device_id = device_id
+        self.kernel = nn.Parameter(torch.empty(feat_dim, num_class))
+        nn.init.normal_(self.kernel, std=0.01)
+        self._init_engine(num_class, s=s, m=m, plus=int(bool(plus)))
+
+    def _sample_margins(self, feats, labels):
+        if bool((labels < 0).any()):
+            raise ValueError("labels == -1 (criterion.py:997) are not supported: CrossEntropyLoss rejects them")
+        if self._margins_override is not None:
+            return self._margins_override
+        # same RNG consumption as criterion.py:1003-1005 / 1116-1118
+        mg = torch.normal(mean=self.m, std=self.std, size=(labels.shape[0], 1), device=feats.device)
+        return mg.clamp(self.m - self.std, self.m + self.std).squeeze(1)
+
+
+class ElasticCosFace(_ElasticBase):
+    """criterion.py:951-1030."""
+    family = "elastic_cos"
+
+    def __init__(self, feat_dim: int, num_class: int, s: float = 64.0, m: float = 0.35, std: float = 0.0125,
+                 plus: bool = False, device_id=None):
+        super().__init__(feat_dim, num_class, s, m, std, plus, device_id)
+
+
+class ElasticArcFace(_ElasticBase):
+    """criterion.py:1054-1154."""
+    family = "elastic_arc"
+
+    def __init__(self, feat_dim: int, num_class: int, s: float = 64.0, m: float = 0.50, std: float = 0.0125,
+                 plus: bool = False, device_id=None):
+        super().__init__(feat_dim, num_class, s, m, std, plus, device_id)
+
+
+class MagFace(_MarginHeadBase):
+    """criterion.py:1178-1301."""
+    family, layout, param_name = "magface", "DC", "kernel"
+
+    def __init__(self, feat_dim: int, num_class: int, s: float = 64.0, easy_margin: bool = True,
+                 l_margin: float = 0.45, u_margin: float = 0.8, l_a: float = 10.0, u_a: float = 110.0,
+                 device_id=None):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.feat_dim, self.num_class, self.s, self.easy_margin = feat_dim, num_class, s, easy_margin
+        self.l_margin, self.u_margin, self.l_a, self.u_a, self.device_id = l_margin, u_margin, l_a, u_a, device_id
+        self.kernel = nn.Parameter(torch.empty(feat_dim, num_class))
+        _insightface_init(self.kernel)
+        self._init_engine(num_class, s=s, easy_margin=int(bool(easy_margin)), l_margin=l_margin, u_margin=u_margin,
+                          l_a=l_a, u_a=u_a)
+
+
+HEAD_CLASSES = dict(
+    arcface=ArcFace, cosface=CosFace, sphereface=SphereFace, mv_am=MV_Softmax, mv_arc=MV_Softmax,
+    curricularface=CurricularFace, adaface=AdaFace, elastic_cos=ElasticCosFace, elastic_arc=ElasticArcFace,
+    magface=MagFace,
+)

@@ -1,0 +1,231 @@
+/*
+ * margin_head.h - C ABI of the B200-native large-margin cosine-softmax head.
+ *
+ * The reference (Lac-quan-yeu-doi/Face-Recognition-Models) has no FFI: the hot path is a set of
+ * Python nn.Modules in main_code/utils/criterion.py called from main_code/utils/model_utils.py:177.
+ * This header is the boundary a maintainer binds with ctypes: plain pointers
+ * and sizes, no torch types.  Every pointer is a DEVICE pointer unless its name ends in _host.
+ * Every function enqueues work on `stream` (a cudaStream_t passed as void*), never allocates,
+ * never synchronises, and returns 0 on success or a negative mh_status; mh_last_error() gives a
+ * thread-local message.  All kernels are compiled for sm_100a only; there is no CPU fallback.
+ *
+ * Path:   x[B,512], W -> normalise -> cos = x^ w^T -> clamp -> margin on the
+ * target column / hard-negative re-weighting -> scale -> softmax cross-entropy (+ top-1/5 rank)
+ * -> dx, dW.
+ */
+#ifndef MARGIN_HEAD_H_
+#define MARGIN_HEAD_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MH_D 512                 /* embedding dimension (config.py:13 FEATURE_DIM)        */
+#define MH_TILE 128              /* B and C are padded to multiples of this in workspaces */
+#define MH_NTILE_FWD 256         /* class-tile width of the tensor-core forward           */
+
+typedef enum mh_status {
+  MH_OK = 0,
+  MH_ERR_ARG = -1,               /* bad shape / null pointer / misalignment */
+  MH_ERR_CUDA = -2,              /* CUDA runtime or driver error            */
+  MH_ERR_UNSUPPORTED = -3        /* e.g. device is not sm_100               */
+} mh_status;
+
+/* One value per reference head class (criterion.py line of the class in the comment). */
+typedef enum mh_family {
+  MH_ARCFACE = 0,                /* criterion.py:232  */
+  MH_COSFACE = 1,                /* criterion.py:137  */
+  MH_SPHEREFACE = 2,             /* criterion.py:12   */
+  MH_MV_AM = 3,                  /* criterion.py:327, margin_type='am'  */
+  MH_MV_ARC = 4,                 /* criterion.py:327, margin_type='arc' */
+  MH_CURRICULAR = 5,             /* criterion.py:491  */
+  MH_ADAFACE = 6,                /* criterion.py:795  */
+  MH_ELASTIC_COS = 7,            /* criterion.py:951  */
+  MH_ELASTIC_ARC = 8,            /* criterion.py:1054 */
+  MH_MAGFACE = 9                 /* criterion.py:1178 */
+} mh_family;
+
+typedef enum mh_layout {
+  MH_LAYOUT_CD = 0,              /* parameter `weight [C, D]` (ArcFace, SphereFace, MV_Softmax) */
+  MH_LAYOUT_DC = 1               /* parameter `kernel [D, C]` (all other heads)                */
+} mh_layout;
+
+typedef enum mh_dtype { MH_F32 = 0, MH_BF16 = 1, MH_F16 = 2 } mh_dtype;
+
+/* Row-parameter planes produced by mh_row_params: rowp[plane * ldp + row], float32. */
+enum {
+  MH_RP_SCALE = 0,    /* logit scale of the row: s, or |x_i| for SphereFace (criterion.py:105)        */
+  MH_RP_THR = 1,      /* hard-negative threshold (MV: criterion.py:424/430, Curricular: :559), +inf   */
+  MH_RP_ZT = 2,       /* target logit z_{i,y_i}                                                       */
+  MH_RP_DZT = 3,      /* d z_{i,y_i} / d cos_raw_{i,y_i} (clamp mask folded in)                       */
+  MH_RP_T = 4,        /* clamped target cosine (pre-margin value at the target column)                */
+  MH_RP_DZT_DN = 5,   /* d z_{i,y_i} / d |x_i| through the margin (MagFace, criterion.py:1264)        */
+  MH_RP_DLG_DN = 6,   /* d loss_g / d |x_i| (MagFace, criterion.py:1235-1238)                         */
+  MH_RP_NORMS = 7,    /* what the reference returns as `norms` (MagFace: clamped, criterion.py:1290)  */
+  MH_RP_PLANES = 8
+};
+
+/* Per-row forward statistics, stats[plane * lds + row], float32 (log2 domain for M/L). */
+enum {
+  MH_ST_M = 0,        /* running max of z*log2(e)                                      */
+  MH_ST_L = 1,        /* sum of exp2(z*log2(e) - M)                                    */
+  MH_ST_CNT = 2,      /* #non-target classes with pre-margin logit > target's (metrics.py:8) */
+  MH_ST_EZ = 3,       /* sum of exp2(z*log2e - M) * u   (SphereFace d|x| term), else 0 */
+  MH_ST_PLANES = 4
+};
+
+/* Per-row results of mh_combine, rowout[plane * ldo + row], float32. */
+enum {
+  MH_RO_LSE2 = 0,     /* log2-sum-exp2 of the row's logits (global over all shards)        */
+  MH_RO_LOSS = 1,     /* lse - z_target (natural log units)                                 */
+  MH_RO_CNT = 2,      /* rank count                                                        */
+  MH_RO_AUX0 = 3,     /* d loss_row / d z_target = P_iy - 1 (feeds the MagFace |x| path)   */
+  MH_RO_AUX1 = 4,     /* sum_j (P_ij - Y_ij) u_ij (SphereFace |x| path), else 0            */
+  MH_RO_PLANES = 5
+};
+
+/* Hyper-parameters: the reference constructor arguments (criterion.py:17-21,141-142,234,334-341,
+ * 496-501,802-809,955-962,1061-1068,1185-1194).  POD, passed by pointer from the host. */
+typedef struct mh_config {
+  int32_t family;        /* mh_family */
+  int32_t easy_margin;   /* ArcFace / MagFace */
+  int32_t sphere_m;      /* SphereFace integer m in 0..5 */
+  int32_t plus;          /* ElasticFace plus (the re-assignment itself is done by the caller) */
+  float s, m;
+  float mv_weight;       /* MV_Softmax */
+  float momentum;        /* CurricularFace */
+  float h, t_alpha;      /* AdaFace */
+  float l_margin, u_margin, l_a, u_a; /* MagFace */
+  float sphere_lambda;   /* SphereFace annealing value for THIS step (host computes, criterion.py:60) */
+  float reserved;
+} mh_config;
+
+/* Mutable head state living on the device: [0]=CurricularFace t, [1]=AdaFace batch_mean,
+ * [2]=AdaFace batch_std, [3]=loss_g of the last forward (MagFace), [4]=the CurricularFace t used by
+ * THIS forward's hard-negative modulation (criterion.py:575; equals [0] when update_state != 0). */
+#define MH_STATE_FLOATS 8
+
+const char* mh_version(void);
+const char* mh_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), else MH_ERR_UNSUPPORTED. */
+int mh_device_check(void);
+
+/* ---- prologues (HBM-bound) ------------------------------------------------------------------ */
+
+/* Replaces F.normalize(self.weight) / F.normalize(self.kernel, dim=0) (criterion.py:65,174,264,404,
+ * 541,864,987,1096,1252).  Reads the fp32 parameter in its own layout (ld = row pitch in elements:
+ * D for CD, C for DC), writes w_hat as bf16 [C_pad, 512] (rows >= C zeroed), optional fp32 copy
+ * w_hat32 [C, 512] (NULL to skip) and inv_norm[C] = 1/max(|w_j|,1e-12). */
+int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, void* w_hat_bf16, int64_t C_pad,
+                  float* w_hat32, float* inv_norm, void* stream);
+
+/* Replaces F.normalize(x) + torch.norm(x) (criterion.py:65,95,173,192,263,298,...) and the target
+ * cosine gather (criterion.py:417,552).  labels are GLOBAL class ids (int64); this shard owns
+ * [c_offset, c_offset + C).  Outputs: x_hat bf16 [B_pad,512] (rows >= B zeroed), x_hat32 fp32
+ * [B,512], xnorm[B], t_raw[B] = <x_hat_i, w_hat_{y_i}> in fp32 (0 when the label is not owned),
+ * label_local[B_pad] (int32; -1 when not owned or row >= B). */
+int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pad, const int64_t* labels,
+                  const float* W, int layout, int64_t C, int64_t ld, int64_t c_offset,
+                  const float* inv_norm, void* x_hat_bf16, float* x_hat32, float* xnorm, float* t_raw,
+                  int32_t* label_local, void* stream);
+
+/* Per-row margin terms + batch-global state updates (CurricularFace EMA criterion.py:570-573,
+ * AdaFace batch statistics criterion.py:876-885, MagFace loss_g criterion.py:1248).  margins may be
+ * NULL except for ElasticFace (one sampled margin per row, criterion.py:1003-1012).  state is
+ * read-modify-written when update_state != 0.  rowp is [MH_RP_PLANES, ldp]. Single small kernel. */
+int mh_row_params(const mh_config* cfg_host, int64_t B, const float* xnorm, const float* t_raw,
+                  const float* margins, float* state, int update_state, float* rowp, int64_t ldp,
+                  void* stream);
+
+/* ---- tensor-core path (bf16 operands, fp32 accumulate, tcgen05 + TMEM + TMA) ------------------ */
+
+/* Number of class tiles the forward writes statistics for, = ceil(C_pad / MH_NTILE_FWD). */
+int64_t mh_fwd_num_tiles(int64_t C_pad);
+
+/* Fused cos-GEMM + margin + online softmax (replaces F.linear/torch.mm at criterion.py:65,176,267,
+ * 408,545,868,990,1100,1256, the elementwise margin passes and nn.CrossEntropyLoss's log-softmax,
+ * model_utils.py:179).  stats_tiles is [num_tiles, MH_ST_PLANES, B_pad]; nothing of size B x C is
+ * written. */
+int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
+                  const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
+                  const int32_t* label_local, const float* state, float* stats_tiles, void* stream);
+
+/* Backward step 1: recompute the logit tiles and write G = (P - Y) * dz/dcos as bf16 [B_pad, C_pad]
+ * (the only B x C object of the path; never the logits).  lse2 = rowout plane MH_RO_LSE2. */
+int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
+                     const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
+                     const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
+                     void* stream);
+
+/* Backward step 2: dx_hat partials = G . w_hat, split over the class dimension.
+ * Returns the number of splits through *n_split_host (call with out == NULL to query).
+ * out is [n_split, B_pad, 512] fp32. */
+int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16,
+                      float* out, int* n_split_host, void* stream);
+
+/* Backward step 3: dw_hat = G^T . x_hat, [C_pad, 512] fp32 (unscaled). */
+int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
+                      float* dw_hat, void* stream);
+
+/* ---- exact fp32 path (SIMT; materialises S = x^ w^T [B, C]; small C, tests, compat mode) ------- */
+
+/* C[M,N] (ldc) = A[M,K] . B[K,N] with arbitrary element strides (row, col) for A and B. fp32 FMA. */
+int mh_sgemm_strided(int64_t M, int64_t N, int64_t K, const float* A, int64_t a_rs, int64_t a_cs,
+                     const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, void* stream);
+
+/* From dense cosines S [B, C] (ld = lds_): per-row statistics as ONE tile (stats [MH_ST_PLANES,
+ * B_pad]) and, when non-NULL, the materialised reference outputs pre [B,C] and logits [B,C]
+ * (criterion.py:197,301,... the 4-tuple's first element). */
+int mh_dense_forward(const mh_config* cfg_host, const float* S, int64_t lds_, int64_t B, int64_t B_pad,
+                     int64_t C, const float* rowp, int64_t ldp, const int32_t* label_local,
+                     const float* state, float* stats, float* pre, float* logits, void* stream);
+
+/* In-place S -> dcos.  If dlogits == NULL: dcos = (P - Y) * dz/dcos using lse2 (fused CE).
+ * Otherwise dcos = dlogits * dz/dcos + dpre * dpre/dcos (compat mode: caller-side loss on the
+ * materialised logits) and rowaux [2, B] receives the AUX0/AUX1 row terms of that upstream grad. */
+int mh_dense_backward_dc(const mh_config* cfg_host, float* S, int64_t lds_, int64_t B, int64_t C,
+                         const float* rowp, int64_t ldp, const int32_t* label_local, const float* state,
+                         const float* lse2, const float* dlogits, const float* dpre, float* rowaux,
+                         void* stream);
+
+/* ---- reductions / finalisers -------------------------------------------------------------------- */
+
+/* Merge per-tile (or per-shard) statistics: stats_in [n_parts, MH_ST_PLANES, lds_] ->
+ * stats_out [MH_ST_PLANES, lds_] (online-softmax merge: max, rescaled sums, counts add). */
+int mh_merge_stats(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds_, float* scratch,
+                   float* stats_out, void* stream);
+/* scratch: [MH_MERGE_BLOCKS, MH_ST_PLANES, lds_] floats */
+#define MH_MERGE_BLOCKS 64
+
+/* Final per-row results from merged statistics + scalars:
+ * rowout [MH_RO_PLANES, ldo]; scalars[0]=mean CE loss, [1]=acc@1 %, [2]=acc@5 % (metrics.py:3-16),
+ * computed over rows [0,B) with divisor B_total (global batch, >= B). */
+int mh_finalize_rows(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B,
+                     int64_t B_total, int sphere, float* rowout, int64_t ldo, float* scalars, void* stream);
+
+/* dx = (dxh - x^ (x^.dxh)) / |x| + dn * x^   with dxh = gz * sum_splits dxhat and
+ * dn = gz * (AUX0 * DZT_DN + AUX1) + g_lossg * DLG_DN  (autograd of F.normalize + the |x| paths of
+ * SphereFace criterion.py:95-105 and MagFace criterion.py:1244-1266).  dxhat is [n_split] partials
+ * of [*, 512] fp32 at stride split_stride floats; aux0/aux1 are the AUX planes (rowout or rowaux).
+ * gscal = {gz, g_lossg} on the device.  dx is written in x_dtype. */
+int mh_norm_backward_x(const float* dxhat, int n_split, int64_t split_stride, const float* x_hat32,
+                       const float* xnorm, const float* rowp, int64_t ldp, const float* aux0,
+                       const float* aux1, const float* gscal, int64_t B, void* dx, int x_dtype,
+                       void* stream);
+
+/* dW_j = g * (dw^_j - w^_j (w^_j . dw^_j)) / |w_j|, written in the parameter's own layout
+ * (ld = row pitch of dW).  w_hat given as bf16 [C_pad,512] or fp32 [C,512] (exactly one non-NULL). */
+int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, const float* w_hat32,
+                       const float* inv_norm, const float* gscal, int64_t C, int layout, float* dW,
+                       int64_t ld, void* stream);
+
+/* gscal[0] = upstream_grad(loss_id) / B_total, gscal[1] = upstream_grad(loss_g): device floats so
+ * that a GradScaler-scaled backward (model_utils.py:185) needs no host sync. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARGIN_HEAD_H_ */

@@ -1,0 +1,29 @@
+"""One fused ArcFace head step for ncu (profiling range limited to the last step)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import face_recognition_models_b200 as pkg  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--C", type=int, default=2_000_000)
+ap.add_argument("--B", type=int, default=1024)
+ap.add_argument("--warmup", type=int, default=2)
+a = ap.parse_args()
+head = pkg.ArcFace(512, a.C, s=64.0, m=0.5, easy_margin=False).cuda()
+with torch.no_grad():
+    head.weight.normal_(0, 0.01)
+x = torch.randn(a.B, 512, device="cuda", requires_grad=True)
+y = torch.randint(0, a.C, (a.B,), device="cuda")
+for _ in range(a.warmup):
+    head.fused_loss(x, y).loss.backward()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+out = head.fused_loss(x, y)
+out.loss.backward()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("loss", float(out.loss))

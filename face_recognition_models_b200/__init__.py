@@ -10,7 +10,8 @@ All compute runs in libmargin_head.so (hand-written sm_100a CUDA behind a C ABI,
 from .heads import (AdaFace, ArcFace, CosFace, CurricularFace, ElasticArcFace, ElasticCosFace, FusedOutput,
                     HEAD_CLASSES, MagFace, MV_Softmax, SphereFace)
 from .functional import HeadEngine, ShardInfo
+from .sharded import ShardedMarginHead, ShardComm, shard_range
 from . import _lib
 
 __all__ = ["AdaFace", "ArcFace", "CosFace", "CurricularFace", "ElasticArcFace", "ElasticCosFace", "FusedOutput",
-           "HEAD_CLASSES", "MagFace", "MV_Softmax", "SphereFace", "HeadEngine", "ShardInfo", "_lib"]
+           "HEAD_CLASSES", "MagFace", "MV_Softmax", "SphereFace", "HeadEngine", "ShardInfo", "ShardedMarginHead", "ShardComm", "shard_range", "_lib"]

@@ -102,7 +102,28 @@ def check(status: int, what: str) -> None:
         raise MarginHeadError(f"{what} failed (status {status}): {msg}")
 
 
+# When set to a list, every call is bracketed by CUDA events on the current (launching) stream and
+# (name, start_event, end_event, n_kernel_launches) is appended: bench.py's per-kernel roofline timing.
+PROFILE = None
+
+
+def _launches(name: str, args) -> int:
+    if name == "mh_merge_stats":
+        return 2 if int(args[1]) >= 256 else 1
+    if name == "mh_tc_backward_dx":
+        return 0 if not getattr(args[4], "value", None) else 1
+    return 1
+
+
 def call(name: str, *args) -> None:
     """Call an int-returning entry point and raise MarginHeadError on a non-zero status."""
     lib = load()
+    if PROFILE is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib, name)(*args), name)
+    e1.record()
+    PROFILE.append((name, e0, e1, _launches(name, args)))

@@ -9,8 +9,8 @@
 //   DX     dx^ partials = G . w^      (A = G K-major,  B = w^ MN-major, split over classes)
 //   DW     dw^          = G^T . x^    (A = G MN-major, B = x^ MN-major)
 //
-// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
-// epilogue (one TMEM lane = one accumulator row per thread).  Tile 128 x 256 x 64, 4 smem stages
+// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11
+// epilogue (thread = one accumulator row x one 128-column half).  Tile 128 x 256 x 64, 4 smem stages
 // (48 KB each), two 256-column TMEM accumulators so the epilogue of tile t overlaps the MMAs of t+1.
 #include "common.cuh"
 #include <cuda.h>
@@ -25,8 +25,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;      // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
 enum { MODE_FWD = 0, MODE_BWD_G = 1, MODE_DX = 2, MODE_DW = 3 };
@@ -187,13 +188,147 @@ __device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t) {
 }
 
 // ---- epilogue helpers -----------------------------------------------------------------------------
+// Family variants of the B x C element transform (compile-time, so the hot loop carries no dead work):
+//   V_PLAIN  no clamp                       (ArcFace, criterion.py:267-301)
+//   V_CLAMP  clamp only                     (CosFace, AdaFace, ElasticFace, MagFace)
+//   V_SPHERE clamp + sum e*u statistic      (SphereFace: logits scale with |x|, criterion.py:105)
+//   V_MV     clamp + c>thr ? w*c+w-1 : c    (MV-Softmax, criterion.py:433-435)
+//   V_CURR   clamp + c>thr ? c*(t+c) : c    (CurricularFace, criterion.py:559,575)
+enum { V_PLAIN = 0, V_CLAMP = 1, V_SPHERE = 2, V_MV = 3, V_CURR = 4, V_NONE = 5 };
+
 struct RowCtx {
   float scale, scale2, thr, t, zt2, dzt, lse2;
   int tcol;          // tile-local target column, or -1
   bool valid;        // row < B
 };
 
-template <int MODE>
+struct FwdAcc {
+  float m, l, ez;
+  int cnt;
+};
+
+template <int V>
+__device__ __forceinline__ float elem_u(float raw, float lo, float hi, float thr, float ha, float hb, float& c_out) {
+  float c = raw;
+  if (V != V_PLAIN) c = fminf(fmaxf(raw, lo), hi);
+  c_out = c;
+  if (V == V_MV) return (c > thr) ? fmaf(ha, c, hb) : c;
+  if (V == V_CURR) return (c > thr) ? c * (ha + c) : c;
+  return c;
+}
+template <int V>
+__device__ __forceinline__ float elem_du(float raw, float c, float thr, float ha) {
+  float du = 1.f;
+  if (V == V_MV) du = (c > thr) ? ha : 1.f;
+  if (V == V_CURR) du = (c > thr) ? (ha + 2.f * c) : 1.f;
+  if (V != V_PLAIN && c != raw) du = 0.f;            // clamp passes gradient only inside [lo, hi]
+  return du;
+}
+
+// One 32-column chunk of the forward: online max / sum-exp (log2 domain), rank count, optional sum e*u.
+template <int V>
+__device__ __forceinline__ void fwd_chunk(uint32_t (&v)[32], int col0, int nvalid, const RowCtx& rc, float lo,
+                                          float hi, float ha, float hb, FwdAcc& acc) {
+  const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid);
+  float umax = -INFINITY;
+  if (!slow) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float c;
+      const float u = elem_u<V>(__uint_as_float(v[k]), lo, hi, rc.thr, ha, hb, c);
+      if (c > rc.t) acc.cnt += 1;
+      umax = fmaxf(umax, u);
+      v[k] = __float_as_uint(u);
+    }
+    const float zmax = umax * rc.scale2;                 // scale2 >= 0, so max z = scale2 * max u
+    if (zmax > acc.m) {
+      const float rs = ex2(acc.m - zmax);
+      acc.l *= rs; acc.ez *= rs; acc.m = zmax;
+    }
+    const float negm = -acc.m;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float u = __uint_as_float(v[k]);
+      const float e = ex2(fmaf(u, rc.scale2, negm));
+      acc.l += e;
+      if (V == V_SPHERE) acc.ez = fmaf(e, u, acc.ez);
+    }
+  } else {
+    // rare path: the chunk holds this row's target column and/or padded classes
+    float z2[32];
+    float zmax = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float c;
+      const float u = elem_u<V>(__uint_as_float(v[k]), lo, hi, rc.thr, ha, hb, c);
+      float z = u * rc.scale2;
+      const int col = col0 + k;
+      if (col == rc.tcol) z = rc.zt2;
+      else if (col < nvalid && c > rc.t) acc.cnt += 1;
+      if (col >= nvalid) z = -INFINITY;
+      z2[k] = z;
+      zmax = fmaxf(zmax, z);
+    }
+    if (zmax > acc.m) {
+      const float rs = ex2(acc.m - zmax);
+      acc.l *= rs; acc.ez *= rs; acc.m = zmax;
+    }
+    if (acc.m > -INFINITY) {
+      const float inv_s2 = (rc.scale2 != 0.f) ? 1.f / rc.scale2 : 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float e = ex2(z2[k] - acc.m);
+        acc.l += e;
+        if (V == V_SPHERE) acc.ez = fmaf(e, fmaxf(z2[k], -1e30f) * inv_s2, acc.ez);   // u = z/scale; 0 * -inf guard
+      }
+    }
+  }
+}
+
+// One 32-column chunk of the backward-G kernel: G = (P - Y) * dz/dcos -> 16 packed bf16 pairs.
+template <int V>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int nvalid, const RowCtx& rc, float lo,
+                                          float hi, float ha, float hb, uint32_t (&pk)[16]) {
+  const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid) || !rc.valid;
+  const float negl = -rc.lse2;
+  if (!slow) {
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      float g2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float raw = __uint_as_float(v[k + h]);
+        float c;
+        const float u = elem_u<V>(raw, lo, hi, rc.thr, ha, hb, c);
+        const float pr = ex2(fmaf(u, rc.scale2, negl));
+        g2[h] = pr * rc.scale * elem_du<V>(raw, c, rc.thr, ha);
+      }
+      __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
+      pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      float g2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float raw = __uint_as_float(v[k + h]);
+        float c;
+        const float u = elem_u<V>(raw, lo, hi, rc.thr, ha, hb, c);
+        float z = u * rc.scale2, dzdc = rc.scale * elem_du<V>(raw, c, rc.thr, ha), yv = 0.f;
+        const int col = col0 + k + h;
+        if (col == rc.tcol) { z = rc.zt2; dzdc = rc.dzt; yv = 1.f; }
+        float g = (ex2(z + negl) - yv) * dzdc;
+        if (col >= nvalid || !rc.valid) g = 0.f;
+        g2[h] = g;
+      }
+      __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
+      pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
+    }
+  }
+}
+
+template <int MODE, int V>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -218,7 +353,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 4);          // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS);     // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -290,10 +425,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue ===============================
-    const int q = warp - EPI_WARP0;                 // TMEM lane quarter == warp % 4
+    // 8 warps: warp%4 selects the TMEM lane quarter (hardware rule), (warp-4)/4 the 128-column half.
+    const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
     const int r = q * 32 + lane;                    // row of the tile owned by this thread
     const MhParams& p = a.p;
-    const float ha = (p.hard_kind == 2) ? a.state[4] : p.hard_a;
+    const float ha = (V == V_CURR) ? a.state[4] : p.hard_a;
+    const float hb = p.hard_b, lo = p.lo, hi = p.hi;
     uint32_t it = 0;
     for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
       const Work w = get_work<MODE>(a, t);
@@ -314,94 +452,66 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         rc.lse2 = (MODE == MODE_BWD_G && rc.valid) ? a.lse2[row] : 0.f;
       }
       const int nvalid = (int)min((int64_t)BN, a.C - (int64_t)w.n0);   // valid class columns in this tile (FWD/BWD_G)
+      const int cbase = half * (BN / 2);
       mbar_wait(bar_tfull + 8 * buf, bphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + cbase;
 
-      float st_m = -INFINITY, st_l = 0.f, st_cnt = 0.f, st_ez = 0.f;
-
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = c * 32;
-        if (MODE == MODE_FWD) {
-          const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid);
-          float z2[32];
-          float zmax = -INFINITY;
-          if (!slow) {
+      FwdAcc acc{-INFINITY, 0.f, 0.f, 0};
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
+      tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              ElemOut e = mh_elem(__uint_as_float(v[k]), p.lo, p.hi, p.hard_kind, rc.thr, ha, p.hard_b);
-              z2[k] = rc.scale2 * e.u;
-              st_cnt += (e.c > rc.t) ? 1.f : 0.f;
-              zmax = fmaxf(zmax, z2[k]);
-            }
+      for (int c = 0; c < (BN / 2) / 32; c += 2) {
+        tmem_ld32(taddr + (c + 1) * 32, vb);               // prefetch the next chunk while this one is processed
+        {
+          const int col0 = cbase + c * 32;
+          if (MODE == MODE_FWD) {
+            fwd_chunk<V>(va, col0, nvalid, rc, lo, hi, ha, hb, acc);
+          } else if (MODE == MODE_BWD_G) {
+            uint32_t pk[16];
+            bwd_chunk<V>(va, col0, nvalid, rc, lo, hi, ha, hb, pk);
+            uint4* dst = reinterpret_cast<uint4*>(a.G + row * a.C_pad + w.n0 + col0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
           } else {
+            float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              ElemOut e = mh_elem(__uint_as_float(v[k]), p.lo, p.hi, p.hard_kind, rc.thr, ha, p.hard_b);
-              float z = rc.scale2 * e.u;
-              const int col = col0 + k;
-              if (col == rc.tcol) z = rc.zt2;
-              else if (col < nvalid) st_cnt += (e.c > rc.t) ? 1.f : 0.f;
-              if (col >= nvalid) z = -INFINITY;
-              z2[k] = z;
-              zmax = fmaxf(zmax, z);
-            }
+            for (int k = 0; k < 8; ++k)
+              reinterpret_cast<uint4*>(dst)[k] = make_uint4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]);
           }
-          if (zmax > st_m) {
-            const float rs = ex2(st_m - zmax);      // st_m = -inf -> 0
-            st_l *= rs; st_ez *= rs; st_m = zmax;
-          }
-          if (st_m > -INFINITY) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float e = ex2(z2[k] - st_m);
-              st_l += e;
-              if (p.scale_is_norm) st_ez = fmaf(e, fmaxf(z2[k], -1e30f), st_ez);   // masked cols: 0 * -inf guard
-            }
-          }
-        } else if (MODE == MODE_BWD_G) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            float g2[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              ElemOut e = mh_elem(__uint_as_float(v[k + h]), p.lo, p.hi, p.hard_kind, rc.thr, ha, p.hard_b);
-              float z = rc.scale2 * e.u, dzdc = rc.scale * e.du, yv = 0.f;
-              const int col = col0 + k + h;
-              if (col == rc.tcol) { z = rc.zt2; dzdc = rc.dzt; yv = 1.f; }
-              float g = (ex2(z - rc.lse2) - yv) * dzdc;
-              if (col >= nvalid || !rc.valid) g = 0.f;
-              g2[h] = g;
-            }
-            __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
-            pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(a.G + row * a.C_pad + w.n0 + col0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-        } else {
-          float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            reinterpret_cast<uint4*>(dst)[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         }
+        tmem_ld_wait();
+        if (c + 2 < (BN / 2) / 32) tmem_ld32(taddr + (c + 2) * 32, va);
+        {
+          const int col0 = cbase + (c + 1) * 32;
+          if (MODE == MODE_FWD) {
+            fwd_chunk<V>(vb, col0, nvalid, rc, lo, hi, ha, hb, acc);
+          } else if (MODE == MODE_BWD_G) {
+            uint32_t pk[16];
+            bwd_chunk<V>(vb, col0, nvalid, rc, lo, hi, ha, hb, pk);
+            uint4* dst = reinterpret_cast<uint4*>(a.G + row * a.C_pad + w.n0 + col0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          } else {
+            float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              reinterpret_cast<uint4*>(dst)[k] = make_uint4(vb[4 * k], vb[4 * k + 1], vb[4 * k + 2], vb[4 * k + 3]);
+          }
+        }
+        if (c + 2 < (BN / 2) / 32) tmem_ld_wait();
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       if (MODE == MODE_FWD) {
-        float* sp = a.stats_tiles + (int64_t)w.n_tile * MH_ST_PLANES * a.B_pad;
-        sp[MH_ST_M * a.B_pad + row] = st_m;
-        sp[MH_ST_L * a.B_pad + row] = st_l;
-        sp[MH_ST_CNT * a.B_pad + row] = st_cnt;
-        // EZ accumulates e * z2 = e * u * scale2 ; store sum e*u
-        sp[MH_ST_EZ * a.B_pad + row] = (p.scale_is_norm && rc.scale2 != 0.f) ? st_ez / rc.scale2 : 0.f;
+        float* sp = a.stats_tiles + ((int64_t)w.n_tile * 2 + half) * MH_ST_PLANES * a.B_pad;
+        sp[MH_ST_M * a.B_pad + row] = acc.m;
+        sp[MH_ST_L * a.B_pad + row] = acc.l;
+        sp[MH_ST_CNT * a.B_pad + row] = (float)acc.cnt;
+        sp[MH_ST_EZ * a.B_pad + row] = (V == V_SPHERE) ? acc.ez : 0.f;
       }
     }
   }
@@ -458,22 +568,42 @@ int num_sms() {
   return n;
 }
 
-template <int MODE>
+template <int MODE, int V>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   int grid = (int)std::min<int64_t>(args.total_tiles, num_sms());
-  tc_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, args);
+  tc_kernel<MODE, V><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, args);
   MH_LAUNCH_OK();
   return MH_OK;
 }
 
+int variant_of(const MhParams& p) {
+  if (p.hard_kind == 1) return V_MV;
+  if (p.hard_kind == 2) return V_CURR;
+  if (p.scale_is_norm) return V_SPHERE;
+  if (p.family == MH_ARCFACE) return V_PLAIN;
+  return V_CLAMP;
+}
+
+template <int MODE>
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
+  switch (variant_of(args.p)) {
+    case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, st);
+    case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, st);
+    case V_SPHERE: return launch<MODE, V_SPHERE>(ta, tb, args, st);
+    case V_MV: return launch<MODE, V_MV>(ta, tb, args, st);
+    default: return launch<MODE, V_CURR>(ta, tb, args, st);
+  }
+}
+
 }  // namespace
 
-extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { return (C_pad + BN - 1) / BN; }
+// two statistics records per 256-wide class tile (one per 128-column epilogue half)
+extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { return 2 * ((C_pad + BN - 1) / BN); }
 
 static int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
   MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % BM == 0, "B_pad must be a multiple of 128");
@@ -498,7 +628,7 @@ extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, 
   a.p = mh_make_params(cfg_host);
   a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
   a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.stats_tiles = stats_tiles;
-  return launch<MODE_FWD>(ta, tb, a, (cudaStream_t)stream);
+  return launch_variant<MODE_FWD>(ta, tb, a, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
@@ -519,7 +649,7 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
   a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
   a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.lse2 = lse2;
   a.G = (__nv_bfloat16*)G_bf16;
-  return launch<MODE_BWD_G>(ta, tb, a, (cudaStream_t)stream);
+  return launch_variant<MODE_BWD_G>(ta, tb, a, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
@@ -543,7 +673,7 @@ extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pa
   a.total_tiles = (int64_t)m_tiles * 2 * n_split;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
-  return launch<MODE_DX>(ta, tb, a, (cudaStream_t)stream);
+  return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
@@ -559,5 +689,5 @@ extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pa
   a.total_tiles = (int64_t)a.m_tiles * 2;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = dw_hat; a.out_split_stride = 0;
-  return launch<MODE_DW>(ta, tb, a, (cudaStream_t)stream);
+  return launch<MODE_DW, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }

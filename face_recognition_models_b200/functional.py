@@ -44,8 +44,10 @@ def sphere_lambda(it: int) -> float:
 
 @dataclass
 class ShardInfo:
-    """Class-dimension sharding (Partial-FC style): this rank owns [c_offset, c_offset + C_local)."""
-    group: object = None
+    """Class-dimension sharding (Partial-FC style): this rank owns [c_offset, c_offset + C_local).
+
+    ``comm`` is a ``sharded.ShardComm`` (the collective plumbing; None when world == 1)."""
+    comm: object = None
     rank: int = 0
     world: int = 1
     c_offset: int = 0
@@ -129,7 +131,7 @@ class HeadEngine:
                _ptr(label_local), st)
         if self.shard.world > 1:
             # every rank needs every row's target cosine (thresholds, EMA); only the owner computed it
-            torch.distributed.all_reduce(t_raw, group=self.shard.group)
+            self.shard.comm.allreduce_sum_(t_raw)
 
         if self.family in ("elastic_cos", "elastic_arc"):
             assert margins is not None and margins.numel() == B
@@ -167,7 +169,7 @@ class HeadEngine:
 
         if self.shard.world > 1:
             all_stats = self._buf("all_stats", (self.shard.world, L.ST_PLANES, B_pad), torch.float32, dev)
-            torch.distributed.all_gather_into_tensor(all_stats, stats, group=self.shard.group)
+            self.shard.comm.allgather_stats(stats, out=all_stats)
             scratch = self._buf("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev)
             L.call("mh_merge_stats", _ptr(all_stats), self.shard.world, B, B_pad, _ptr(scratch), _ptr(stats), st)
 
@@ -230,8 +232,7 @@ class HeadEngine:
             assert B % R == 0
             Bl = B // R
             full = part[:, :B].sum(dim=0) if n_split > 1 else part[0, :B]
-            mine = torch.empty((Bl, L.D), dtype=torch.float32, device=dev)
-            torch.distributed.reduce_scatter_tensor(mine, full.contiguous(), group=self.shard.group)
+            mine = self.shard.comm.reduce_scatter_rows(full.contiguous())
             r0 = self.shard.rank * Bl
             dx = torch.empty((Bl, L.D), dtype=ctx["x_dtype"], device=dev)
             rowp_off = ctx["rowp"][:, r0:]

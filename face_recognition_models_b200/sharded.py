@@ -1,0 +1,157 @@
+"""Class-sharded (Partial-FC style) margin head: one process per GPU, NCCL over NVLink.
+
+The class-centre matrix is split along C across the ranks of ``group`` (the reference's dead
+``device_id`` path chunks W the same way, criterion.py:271, but copies tensors every step and has no
+backward-side collective).  Per step and rank:
+
+  1. all-gather  x, labels                      -> every rank sees the global batch  B_g = R * B
+  2. all-reduce  (SUM) of the target cosines    -> owner rank contributes, others 0 (thresholds/EMA need all rows)
+  3. local fused forward on [B_g x C/R]         -> per-row (max, sum-exp, rank-count, e*u)
+  4. all-gather  of the row statistics + merge  -> global log-sum-exp; loss = mean over B_g
+  5. local fused backward                       -> dW for the local shard (no collective: W is model-parallel)
+  6. reduce-scatter (SUM) of dx^ [B_g, 512]     -> each rank's own B rows, then normalise-backward
+
+Scale convention: the loss is the mean over the GLOBAL batch.  dW uses 1/B_g.  The returned dx is
+d(global-mean loss)/dx_local multiplied by ``dx_scale`` (default 1).  When the backbone is wrapped in
+DDP (which averages parameter gradients over ranks) pass ``dx_scale=world_size`` so the backbone
+gradient equals the single-process gradient on the concatenated batch (InsightFace Partial-FC convention).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib as L
+from .functional import HeadEngine, ShardInfo
+from .heads import HEAD_CLASSES, FusedOutput
+
+
+def shard_range(num_classes: int, world: int, rank: int) -> Tuple[int, int]:
+    """[begin, end) of the classes owned by ``rank``: equal chunks of ceil(C/R), last one ragged."""
+    per = (num_classes + world - 1) // world
+    b = min(num_classes, rank * per)
+    e = min(num_classes, b + per)
+    return b, e
+
+
+class ShardComm:
+    """The four exchanges of the sharded head, backend-agnostic (NCCL on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._backend = dist.get_backend(group) if dist.is_initialized() else "none"
+
+    def gather_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """all-gather along dim 0 (x [B,512] -> [R*B,512]; labels [B] -> [R*B])."""
+        if self.world == 1:
+            return t
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allgather_stats(self, stats: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[planes, B_pad] per rank -> [R, planes, B_pad]."""
+        if self.world == 1:
+            return stats.unsqueeze(0)
+        if out is None:
+            out = torch.empty((self.world,) + tuple(stats.shape), dtype=stats.dtype, device=stats.device)
+        # concatenation along dim 0 is what every backend accepts: view [R, planes, B] as [R*planes, B]
+        dist.all_gather_into_tensor(out.view(-1, stats.shape[-1]), stats.contiguous(), group=self.group)
+        return out
+
+    def reduce_scatter_rows(self, full: torch.Tensor) -> torch.Tensor:
+        """SUM over ranks of [R*B, 512], returning this rank's [B, 512] slice."""
+        if self.world == 1:
+            return full
+        Bl = full.shape[0] // self.world
+        if self._backend == "gloo":           # gloo has no reduce_scatter: all-reduce then slice
+            f = full.clone()
+            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group)
+            return f[self.rank * Bl:(self.rank + 1) * Bl].contiguous()
+        out = torch.empty((Bl,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+
+class _ShardedFusedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_local, W_local, labels_local, head, margins_local):
+        comm: ShardComm = head.comm
+        x_g = comm.gather_rows(x_local.contiguous())
+        y_g = comm.gather_rows(labels_local.contiguous().to(torch.int64))
+        margins_g = comm.gather_rows(margins_local.contiguous()) if margins_local is not None else None
+        c = head.engine.forward(x_g, W_local, y_g, head._mh_state, margins_g, update_state=True)
+        ctx.head = head
+        ctx.c = c
+        ctx.B_local = x_local.shape[0]
+        sc = c["scalars"]
+        r0 = comm.rank * ctx.B_local
+        norms = c["rowp"][L.RP["NORMS"], r0:r0 + ctx.B_local].clone().unsqueeze(1)
+        loss, loss_g, acc1, acc5 = sc[0].clone(), head._mh_state[3].clone(), sc[1].clone(), sc[2].clone()
+        ctx.mark_non_differentiable(norms, acc1, acc5)
+        return loss, loss_g, acc1, acc5, norms
+
+    @staticmethod
+    def backward(ctx, g_loss, g_lossg, _a1, _a5, _n):
+        head = ctx.head
+        if g_loss is None:
+            g_loss = torch.zeros((), device=ctx.c["x_hat"].device)
+        dx, dW = head.engine.backward(ctx.c, g_loss, g_lossg, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        if dx is not None and head.dx_scale != 1.0:
+            dx = dx * head.dx_scale
+        return dx, dW, None, None, None
+
+
+class ShardedMarginHead(nn.Module):
+    """Any of the reference head families with the class dimension sharded over ``group``.
+
+    ``ctor_kwargs`` are the reference constructor's keyword arguments other than the two size
+    arguments (e.g. ``s=64.0, m=0.5, easy_margin=False`` for ArcFace).  The local parameter keeps the
+    reference's name and layout (``weight [C_local, D]`` / ``kernel [D, C_local]``).
+    """
+
+    def __init__(self, family: str, num_classes: int, group=None, mode: str = "tc", dx_scale: float = 1.0,
+                 **ctor_kwargs):
+        super().__init__()
+        self.family = family
+        self.num_classes = num_classes
+        self.comm = ShardComm(group)
+        self.dx_scale = float(dx_scale)
+        b, e = shard_range(num_classes, self.comm.world, self.comm.rank)
+        self.c_begin, self.c_end = b, e
+        cls = HEAD_CLASSES[family]
+        if family in ("mv_am", "mv_arc"):
+            ctor_kwargs = dict(ctor_kwargs, margin_type="am" if family == "mv_am" else "arc")
+        # build the local shard with the reference initialisation, then rebind its engine to the shard
+        self.local = cls(512, e - b, **ctor_kwargs)
+        self.local._engine.shard = ShardInfo(comm=self.comm, rank=self.comm.rank, world=self.comm.world, c_offset=b)
+        self.local._engine.mode = mode
+        self.engine: HeadEngine = self.local._engine
+
+    @property
+    def _mh_state(self):
+        return self.local._mh_state
+
+    def shard_parameter(self) -> torch.Tensor:
+        return self.local._param()
+
+    def fused_loss(self, feats: torch.Tensor, labels: torch.Tensor) -> FusedOutput:
+        self.local._check(feats, labels)
+        self.local._pre_forward(feats)
+        margins = self.local._sample_margins(feats, labels)
+        self.local._push_state()
+        out = _ShardedFusedLossFn.apply(feats, self.local._param(), labels, self, margins)
+        self.local._pull_state()
+        return FusedOutput(*out)
+
+    forward = fused_loss

@@ -142,7 +142,7 @@ int mh_row_params(const mh_config* cfg_host, int64_t B, const float* xnorm, cons
 
 /* ---- tensor-core path (bf16 operands, fp32 accumulate, tcgen05 + TMEM + TMA) ------------------ */
 
-/* Number of class tiles the forward writes statistics for, = ceil(C_pad / MH_NTILE_FWD). */
+/* Number of statistics records the forward writes per row, = 2 * ceil(C_pad / MH_NTILE_FWD). */
 int64_t mh_fwd_num_tiles(int64_t C_pad);
 
 /* Fused cos-GEMM + margin + online softmax (replaces F.linear/torch.mm at criterion.py:65,176,267,

@@ -6,8 +6,11 @@
 //          Nothing of size B x C is written (replaces criterion.py:267-301 & siblings +
 //          nn.CrossEntropyLoss, model_utils.py:179, + accuracy, metrics.py:3-16).
 //   BWD_G  recompute the S tile -> G = (P - Y) * dz/dcos as bf16 [B_pad, C_pad].
-//   DX     dx^ partials = G . w^      (A = G K-major,  B = w^ MN-major, split over classes)
-//   DW     dw^          = G^T . x^    (A = G MN-major, B = x^ MN-major)
+//          Also accumulates r_j = sum_i G_ij * cos_ij (= w^_j . dw^_j), the normalise-backward projection.
+//   DX     dx^ partials = G . w^      (A = G K-major,  B = w^ MN-major, split over classes; one 128 x 512
+//          accumulator = all 512 TMEM columns per CTA, so every G byte is read by exactly one CTA)
+//   DW     dw^          = G^T . x^    (A = G MN-major, B = x^ MN-major), raw fp32 output
+//   DWF    same GEMM, epilogue writes dW_j = g (dw^_j - w^_j r_j) / |w_j| straight into the parameter layout
 //
 // CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11
 // epilogue (thread = one accumulator row x one 128-column half).  Tile 128 x 256 x 64, 4 smem stages
@@ -20,17 +23,29 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64, MAX_STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;      // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// Output staging for coalesced global stores (BWD_G: bf16 G rows, DW: fp32 dw^ rows): per epilogue warp
+// 32 rows x 256 B (+16 B pad per row against bank conflicts).  Those two modes run 3 pipeline stages.
+constexpr int STG_ROW_BYTES = 256 + 16;
+constexpr int STG_WARP_BYTES = 32 * STG_ROW_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
-enum { MODE_FWD = 0, MODE_BWD_G = 1, MODE_DX = 2, MODE_DW = 3 };
+enum { MODE_FWD = 0, MODE_BWD_G = 1, MODE_DX = 2, MODE_DW = 3, MODE_DWF = 4 };
+constexpr bool mode_stages_out(int mode) { return mode == MODE_BWD_G || mode == MODE_DW || mode == MODE_DWF; }
+constexpr int mode_bn(int mode) { return mode == MODE_DX ? 512 : 256; }          // accumulator columns per tile
+constexpr int mode_nbuf(int mode) { return mode == MODE_DX ? 1 : 2; }            // TMEM accumulators in flight
+constexpr int mode_stages(int mode) { return mode == MODE_DX ? 2 : (mode_stages_out(mode) ? 3 : 4); }
+constexpr int mode_stage_bytes(int mode) { return A_STAGE_BYTES + mode_bn(mode) * BK * 2; }
+constexpr int mode_smem_bytes(int mode) {
+  return mode_stages(mode) * mode_stage_bytes(mode) + 1024 /*align slack*/ + 256 /*barriers*/ +
+         (mode_stages_out(mode) ? 8 * STG_WARP_BYTES : 0);
+}
+static_assert(mode_smem_bytes(MODE_BWD_G) <= 232448 && mode_smem_bytes(MODE_FWD) <= 232448 &&
+              mode_smem_bytes(MODE_DX) <= 232448, "smem budget");
 
 struct TcArgs {
   int m_tiles, n_tiles, n_split, k_blocks_total, k_blocks_per_split;
@@ -46,6 +61,12 @@ struct TcArgs {
   __nv_bfloat16* G;
   float* out;
   int64_t out_split_stride;
+  float* rsum;                 // BWD_G: r_j accumulation target [C_pad] (zeroed by the caller); DWF: read
+  const __nv_bfloat16* w_hat;  // DWF
+  const float* inv_norm;       // DWF
+  const float* gscal;          // DWF
+  int layout;                  // DWF: parameter layout of dW
+  int64_t ld;                  // DWF: row pitch of dW
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -172,11 +193,9 @@ __device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t) {
     int m = (int)(t % a.m_tiles), n = (int)(t / a.m_tiles);
     w.m0 = m * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK; w.n_tile = n;
   } else if (MODE == MODE_DX) {
-    int per = a.m_tiles * 2;
-    int q = (int)(t % per);
-    w.split = (int)(t / per);
-    w.m0 = (q % a.m_tiles) * BM;
-    w.n0 = (q / a.m_tiles) * BN;
+    w.split = (int)(t / a.m_tiles);
+    w.m0 = (int)(t % a.m_tiles) * BM;
+    w.n0 = 0;
     w.kb0 = w.split * a.k_blocks_per_split;
     w.kb1 = min(a.k_blocks_total, w.kb0 + a.k_blocks_per_split);
   } else {
@@ -285,10 +304,27 @@ __device__ __forceinline__ void fwd_chunk(uint32_t (&v)[32], int col0, int nvali
   }
 }
 
-// One 32-column chunk of the backward-G kernel: G = (P - Y) * dz/dcos -> 16 packed bf16 pairs.
+// Column sums over the 32 lanes of a warp of a 32-register array: on return lane L holds sum_lanes x[L].
+// Transposed butterfly: 31 shuffles, no shared memory.
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = upper ? x[j] : x[j + s];
+      const float keep = upper ? x[j + s] : x[j];
+      x[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
+
+// One 32-column chunk of the backward-G kernel: G = (P - Y) * dz/dcos -> 16 packed bf16 pairs, and
+// q = G * cos_raw left in qv[] for the column sums r_j = sum_i G_ij cos_ij (= w^_j . dw^_j).
 template <int V>
 __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int nvalid, const RowCtx& rc, float lo,
-                                          float hi, float ha, float hb, uint32_t (&pk)[16]) {
+                                          float hi, float ha, float hb, uint32_t (&pk)[16], float (&qv)[32]) {
   const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid) || !rc.valid;
   const float negl = -rc.lse2;
   if (!slow) {
@@ -302,6 +338,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int
         const float u = elem_u<V>(raw, lo, hi, rc.thr, ha, hb, c);
         const float pr = ex2(fmaf(u, rc.scale2, negl));
         g2[h] = pr * rc.scale * elem_du<V>(raw, c, rc.thr, ha);
+        qv[k + h] = g2[h] * raw;
       }
       __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
       pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
@@ -321,6 +358,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int
         float g = (ex2(z + negl) - yv) * dzdc;
         if (col >= nvalid || !rc.valid) g = 0.f;
         g2[h] = g;
+        qv[k + h] = g * raw;
       }
       __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
       pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
@@ -331,16 +369,22 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int
 template <int MODE, int V>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  constexpr int STAGES = mode_stages(MODE);
+  constexpr int STAGE_BYTES = mode_stage_bytes(MODE);
+  constexpr int BNT = mode_bn(MODE);                 // accumulator columns of one tile (256, DX: 512)
+  constexpr int NBUF = mode_nbuf(MODE);
+  constexpr bool IS_DW = (MODE == MODE_DW || MODE == MODE_DWF);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
   uint8_t* tiles_ptr = smem_raw + (tiles_base - raw_addr);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + STAGES * STAGE_BYTES);
+  uint8_t* stg_all = tiles_ptr + STAGES * STAGE_BYTES + 256;        // output staging (BWD_G / DW / DWF only)
   const uint32_t bar_full = smem_u32(bars);                         // [STAGES]
-  const uint32_t bar_empty = bar_full + 8 * STAGES;                 // [STAGES]
-  const uint32_t bar_tfull = bar_empty + 8 * STAGES;                // [2]
+  const uint32_t bar_empty = bar_full + 8 * MAX_STAGES;             // [STAGES]
+  const uint32_t bar_tfull = bar_empty + 8 * MAX_STAGES;            // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -363,8 +407,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  constexpr bool A_MN = (MODE == MODE_DW);
-  constexpr bool B_MN = (MODE == MODE_DX || MODE == MODE_DW);
+  constexpr bool A_MN = IS_DW;
+  constexpr bool B_MN = (MODE == MODE_DX || IS_DW);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -388,7 +432,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tma_load_2d(sb, &tmB, fb, kb * BK, w.n0);                       // box [64 k][256 rows]
           } else {
 #pragma unroll
-            for (int bx = 0; bx < BN / 64; ++bx) tma_load_2d(sb + bx * 8192, &tmB, fb, w.n0 + 64 * bx, kb * BK);
+            for (int bx = 0; bx < BNT / 64; ++bx) tma_load_2d(sb + bx * 8192, &tmB, fb, w.n0 + 64 * bx, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -402,7 +446,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t it = 0;
       for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
         const Work w = get_work<MODE>(a, t);
-        const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+        const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
         mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);                       // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
@@ -414,8 +458,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? desc_mnmajor(sa, k) : desc_kmajor(sa, k);
-            const uint64_t db = B_MN ? desc_mnmajor(sb, k) : desc_kmajor(sb, k);
-            umma_bf16(tmem_d, da, db, idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > w.kb0 || k > 0) ? 1u : 0u;
+#pragma unroll
+            for (int nh = 0; nh < BNT / BN; ++nh) {                       // DX: two N=256 halves of the 512-wide tile
+              const uint32_t sbh = sb + nh * (BN / 64) * 8192;
+              const uint64_t db = B_MN ? desc_mnmajor(sbh, k) : desc_kmajor(sbh, k);
+              umma_bf16(tmem_d + nh * BN, da, db, idesc, acc);
+            }
           }
           umma_commit(bar_empty + 8 * stage);                              // frees the smem stage when MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -425,17 +474,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp >= EPI_WARP0) {
     // =============================== epilogue ===============================
-    // 8 warps: warp%4 selects the TMEM lane quarter (hardware rule), (warp-4)/4 the 128-column half.
+    // 8 warps: warp%4 selects the TMEM lane quarter (hardware rule), (warp-4)/4 the column half.
     const int q = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;
     const int r = q * 32 + lane;                    // row of the tile owned by this thread
+    constexpr int NCHUNK = (BNT / 2) / 32;          // 32-column chunks per warp (4, DX: 8)
     const MhParams& p = a.p;
     const float ha = (V == V_CURR) ? a.state[4] : p.hard_a;
     const float hb = p.hard_b, lo = p.lo, hi = p.hi;
     uint32_t it = 0;
     for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
       const Work w = get_work<MODE>(a, t);
-      const uint32_t buf = it & 1, bphase = (it >> 1) & 1;
+      const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
       const int64_t row = (int64_t)w.m0 + r;
       RowCtx rc;
       rc.valid = true; rc.tcol = -1;
@@ -451,61 +501,125 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (y >= w.n0 && y < w.n0 + BN) rc.tcol = y - w.n0;
         rc.lse2 = (MODE == MODE_BWD_G && rc.valid) ? a.lse2[row] : 0.f;
       }
+      // DWF: this thread owns class `row`; dW_j = coef * (dw^_j - w^_j * rj)
+      float dwf_rj = 0.f, dwf_coef = 0.f;
+      bool dwf_ok = false;
+      if (MODE == MODE_DWF) {
+        dwf_ok = row < a.C;
+        if (dwf_ok) {
+          dwf_rj = a.rsum[row];
+          dwf_coef = a.gscal[0] * a.inv_norm[row];
+        }
+      }
       const int nvalid = (int)min((int64_t)BN, a.C - (int64_t)w.n0);   // valid class columns in this tile (FWD/BWD_G)
-      const int cbase = half * (BN / 2);
+      const int cbase = half * (BNT / 2);
       mbar_wait(bar_tfull + 8 * buf, bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + cbase;
 
       FwdAcc acc{-INFINITY, 0.f, 0.f, 0};
+      uint8_t* stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;      // this warp's [32][272 B] staging rows
       uint32_t va[32], vb[32];
       tmem_ld32(taddr, va);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < (BN / 2) / 32; c += 2) {
-        tmem_ld32(taddr + (c + 1) * 32, vb);               // prefetch the next chunk while this one is processed
-        {
-          const int col0 = cbase + c * 32;
-          if (MODE == MODE_FWD) {
-            fwd_chunk<V>(va, col0, nvalid, rc, lo, hi, ha, hb, acc);
-          } else if (MODE == MODE_BWD_G) {
-            uint32_t pk[16];
-            bwd_chunk<V>(va, col0, nvalid, rc, lo, hi, ha, hb, pk);
-            uint4* dst = reinterpret_cast<uint4*>(a.G + row * a.C_pad + w.n0 + col0);
+      for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t (&cur)[32] = (c & 1) ? vb : va;
+        uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+        if (c + 1 < NCHUNK) tmem_ld32(taddr + (c + 1) * 32, nxt);   // prefetch while this chunk is processed
+        const int col0 = cbase + c * 32;
+        if (MODE == MODE_FWD) {
+          fwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc);
+        } else if (MODE == MODE_BWD_G) {
+          uint32_t pk[16];
+          float qv[32];
+          bwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, pk, qv);
+          uint4* dst = reinterpret_cast<uint4*>(stg + lane * STG_ROW_BYTES + c * 64);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-          } else {
-            float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              reinterpret_cast<uint4*>(dst)[k] = make_uint4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]);
+          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          if (a.rsum) {
+            const float cs = warp_colsum32(qv, lane);                   // lane L: sum over this warp's 32 rows, column col0+L
+            atomicAdd(a.rsum + w.n0 + col0 + lane, cs);
           }
-        }
-        tmem_ld_wait();
-        if (c + 2 < (BN / 2) / 32) tmem_ld32(taddr + (c + 2) * 32, va);
-        {
-          const int col0 = cbase + (c + 1) * 32;
-          if (MODE == MODE_FWD) {
-            fwd_chunk<V>(vb, col0, nvalid, rc, lo, hi, ha, hb, acc);
-          } else if (MODE == MODE_BWD_G) {
-            uint32_t pk[16];
-            bwd_chunk<V>(vb, col0, nvalid, rc, lo, hi, ha, hb, pk);
-            uint4* dst = reinterpret_cast<uint4*>(a.G + row * a.C_pad + w.n0 + col0);
+        } else if (MODE == MODE_DW || (MODE == MODE_DWF && a.layout == MH_LAYOUT_CD)) {
+          float o[32];
+          if (MODE == MODE_DWF) {
+            const uint4* wsrc = reinterpret_cast<const uint4*>(a.w_hat + row * MH_D + w.n0 + col0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              uint4 wq = dwf_ok ? __ldg(wsrc + k4) : make_uint4(0u, 0u, 0u, 0u);
+              const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+                const int k = k4 * 8 + e * 2;
+                o[k] = (__uint_as_float(cur[k]) - wf.x * dwf_rj) * dwf_coef;
+                o[k + 1] = (__uint_as_float(cur[k + 1]) - wf.y * dwf_rj) * dwf_coef;
+              }
+            }
           } else {
-            float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              reinterpret_cast<uint4*>(dst)[k] = make_uint4(vb[4 * k], vb[4 * k + 1], vb[4 * k + 2], vb[4 * k + 3]);
+            for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(cur[k]);
           }
+          float4* dst = reinterpret_cast<float4*>(stg + lane * STG_ROW_BYTES + (c & 1) * 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+          if (c & 1) {
+            // two chunks (64 fp32 columns = 256 B per row) staged: write them out as full 128 B lines,
+            // 16 lanes per row, 2 rows per store instruction
+            __syncwarp();
+            const int64_t opitch = (MODE == MODE_DWF) ? a.ld : (int64_t)MH_D;
+            const int64_t rbase = (int64_t)w.m0 + q * 32;
+            float* obase = a.out + rbase * opitch + w.n0 + cbase + (c - 1) * 32;
+#pragma unroll
+            for (int i2 = 0; i2 < 16; ++i2) {
+              const int rr = 2 * i2 + (lane >> 4);
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * STG_ROW_BYTES + (lane & 15) * 16);
+              if (MODE == MODE_DW || rbase + rr < a.C)
+                *reinterpret_cast<uint4*>(obase + (int64_t)rr * opitch + (lane & 15) * 4) = val;
+            }
+            __syncwarp();
+          }
+        } else if (MODE == MODE_DWF) {
+          // parameter layout [D, C]: for a fixed d the 32 lanes are 32 consecutive classes -> coalesced directly
+          const uint4* wsrc = reinterpret_cast<const uint4*>(a.w_hat + row * MH_D + w.n0 + col0);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            uint4 wq = dwf_ok ? __ldg(wsrc + k4) : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+              const int k = k4 * 8 + e * 2;
+              if (dwf_ok) {
+                a.out[(int64_t)(w.n0 + col0 + k) * a.ld + row] = (__uint_as_float(cur[k]) - wf.x * dwf_rj) * dwf_coef;
+                a.out[(int64_t)(w.n0 + col0 + k + 1) * a.ld + row] = (__uint_as_float(cur[k + 1]) - wf.y * dwf_rj) * dwf_coef;
+              }
+            }
+          }
+        } else {
+          float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            reinterpret_cast<uint4*>(dst)[k] = make_uint4(cur[4 * k], cur[4 * k + 1], cur[4 * k + 2], cur[4 * k + 3]);
         }
-        if (c + 2 < (BN / 2) / 32) tmem_ld_wait();
+        if (c + 1 < NCHUNK) tmem_ld_wait();
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (MODE == MODE_BWD_G) {
+        // staged [32 rows][128 bf16 = 256 B] -> global, full lines: 16 lanes per row, 2 rows per instruction
+        __nv_bfloat16* obase = a.G + ((int64_t)w.m0 + q * 32) * a.C_pad + w.n0 + cbase;
+#pragma unroll
+        for (int i2 = 0; i2 < 16; ++i2) {
+          const int rr = 2 * i2 + (lane >> 4);
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * STG_ROW_BYTES + (lane & 15) * 16);
+          *reinterpret_cast<uint4*>(obase + (int64_t)rr * a.C_pad + (lane & 15) * 8) = val;
+        }
+        __syncwarp();
+      }
       if (MODE == MODE_FWD) {
         float* sp = a.stats_tiles + ((int64_t)w.n_tile * 2 + half) * MH_ST_PLANES * a.B_pad;
         sp[MH_ST_M * a.B_pad + row] = acc.m;
@@ -572,11 +686,11 @@ template <int MODE, int V>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, mode_smem_bytes(MODE)));
     attr_set = true;
   }
   int grid = (int)std::min<int64_t>(args.total_tiles, num_sms());
-  tc_kernel<MODE, V><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, args);
+  tc_kernel<MODE, V><<<grid, NUM_THREADS, mode_smem_bytes(MODE), st>>>(ta, tb, args);
   MH_LAUNCH_OK();
   return MH_OK;
 }
@@ -634,7 +748,7 @@ extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, 
 extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                                 const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                                 const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
-                                void* stream) {
+                                float* r_colsum, void* stream) {
   MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && lse2 && G_bf16, "null pointer");
   if (int e = check_common(B, B_pad, C, C_pad)) return e;
   MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
@@ -649,6 +763,8 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
   a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
   a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.lse2 = lse2;
   a.G = (__nv_bfloat16*)G_bf16;
+  a.rsum = r_colsum;
+  if (r_colsum) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
   return launch_variant<MODE_BWD_G>(ta, tb, a, (cudaStream_t)stream);
 }
 
@@ -657,7 +773,7 @@ extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pa
   MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
   const int m_tiles = (int)(B_pad / BM);
   const int kb_total = (int)(C_pad / BK);
-  int n_split = std::max(1, num_sms() / (m_tiles * 2));
+  int n_split = std::max(1, num_sms() / m_tiles);
   n_split = std::min(n_split, kb_total);
   int per = (kb_total + n_split - 1) / n_split;
   n_split = (kb_total + per - 1) / per;                 // no empty splits
@@ -668,9 +784,9 @@ extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pa
   if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, BM)) return e;          // A = G, K-major (K = class)
   if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, 64)) return e;       // B = w^, MN-major boxes [64 k][64 d]
   TcArgs a{};
-  a.m_tiles = m_tiles; a.n_tiles = 2; a.n_split = n_split;
+  a.m_tiles = m_tiles; a.n_tiles = 1; a.n_split = n_split;
   a.k_blocks_total = kb_total; a.k_blocks_per_split = per;
-  a.total_tiles = (int64_t)m_tiles * 2 * n_split;
+  a.total_tiles = (int64_t)m_tiles * n_split;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
   return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
@@ -690,4 +806,25 @@ extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pa
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = dw_hat; a.out_split_stride = 0;
   return launch<MODE_DW, V_NONE>(ta, tb, a, (cudaStream_t)stream);
+}
+
+extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
+                                       const void* w_hat_bf16, const float* inv_norm, const float* r_colsum,
+                                       const float* gscal, int layout, float* dW, int64_t ld, void* stream) {
+  MH_CHECK_ARG(G_bf16 && x_hat_bf16 && w_hat_bf16 && inv_norm && r_colsum && gscal && dW, "null pointer");
+  MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0 && C > 0 && C <= C_pad, "bad padded shape");
+  MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
+  MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)dW & 15) == 0), "CD dW must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, 64)) return e;
+  if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;
+  TcArgs a{};
+  a.m_tiles = (int)(C_pad / BM); a.n_tiles = 2; a.n_split = 1;
+  a.k_blocks_total = (int)(B_pad / BK); a.k_blocks_per_split = a.k_blocks_total;
+  a.total_tiles = (int64_t)a.m_tiles * 2;
+  a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C;
+  a.out = dW; a.out_split_stride = 0;
+  a.rsum = const_cast<float*>(r_colsum); a.w_hat = (const __nv_bfloat16*)w_hat_bf16; a.inv_norm = inv_norm;
+  a.gscal = gscal; a.layout = layout; a.ld = ld;
+  return launch<MODE_DWF, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }

@@ -204,8 +204,9 @@ class HeadEngine:
                    _ptr(ctx["label_local"]), _ptr(state), _ptr(lse2), _ptr(None), _ptr(None), _ptr(None), st)
             return self._exact_grads(ctx, S, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]], need_dx, need_dw)
         G = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
+        rsum = self._buf("r_colsum", (C_pad,), torch.float32, dev) if need_dw else None
         L.call("mh_tc_backward_g", C.byref(self.cfg), _ptr(ctx["x_hat"]), B, B_pad, _ptr(ctx["w_hat"]), Cn, C_pad,
-               _ptr(rowp), B_pad, _ptr(ctx["label_local"]), _ptr(state), _ptr(lse2), _ptr(G), st)
+               _ptr(rowp), B_pad, _ptr(ctx["label_local"]), _ptr(state), _ptr(lse2), _ptr(G), _ptr(rsum), st)
         dx = dW = None
         if need_dx:
             ns = C.c_int(0)
@@ -215,11 +216,9 @@ class HeadEngine:
             L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(ctx["w_hat"]), _ptr(part), C.byref(ns), st)
             dx = self._finish_dx(ctx, part, n_split, B_pad * L.D, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
         if need_dw:
-            dw_hat = self._buf("dw_hat", (C_pad, L.D), torch.float32, dev)
-            L.call("mh_tc_backward_dw", _ptr(G), B_pad, C_pad, _ptr(ctx["x_hat"]), _ptr(dw_hat), st)
             dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
-            L.call("mh_norm_backward_w", _ptr(dw_hat), _ptr(ctx["w_hat"]), _ptr(None), _ptr(ctx["inv_norm"]), _ptr(gscal),
-                   Cn, self.layout, _ptr(dW), ctx["ld"], st)
+            L.call("mh_tc_backward_dw_fused", _ptr(G), B_pad, Cn, C_pad, _ptr(ctx["x_hat"]), _ptr(ctx["w_hat"]),
+                   _ptr(ctx["inv_norm"]), _ptr(rsum), _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], st)
         return dx, dW
 
     def _finish_dx(self, ctx, part, n_split, split_stride, gscal, aux0, aux1):

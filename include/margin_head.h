@@ -154,11 +154,13 @@ int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, 
                   const int32_t* label_local, const float* state, float* stats_tiles, void* stream);
 
 /* Backward step 1: recompute the logit tiles and write G = (P - Y) * dz/dcos as bf16 [B_pad, C_pad]
- * (the only B x C object of the path; never the logits).  lse2 = rowout plane MH_RO_LSE2. */
+ * (the only B x C object of the path; never the logits).  lse2 = rowout plane MH_RO_LSE2.
+ * r_colsum [C_pad] (may be NULL) receives r_j = sum_i G_ij * cos_ij = w^_j . dw^_j, the projection term of
+ * the normalise-backward of W; it is zeroed (stream-ordered) before the kernel accumulates into it. */
 int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                      const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                      const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
-                     void* stream);
+                     float* r_colsum, void* stream);
 
 /* Backward step 2: dx_hat partials = G . w_hat, split over the class dimension.
  * Returns the number of splits through *n_split_host (call with out == NULL to query).
@@ -169,6 +171,13 @@ int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const vo
 /* Backward step 3: dw_hat = G^T . x_hat, [C_pad, 512] fp32 (unscaled). */
 int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
                       float* dw_hat, void* stream);
+
+/* Backward step 3, fused with the normalise-backward of W (autograd of F.normalize(self.weight), criterion.py:264):
+ * dW_j = gscal[0] * (dw^_j - w^_j * r_j) / |w_j| written straight into the parameter layout (ld = row pitch);
+ * replaces mh_tc_backward_dw + mh_norm_backward_w and their 4*C*d-byte dw_hat round trip. */
+int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
+                            const void* w_hat_bf16, const float* inv_norm, const float* r_colsum,
+                            const float* gscal, int layout, float* dW, int64_t ld, void* stream);
 
 /* ---- exact fp32 path (SIMT; materialises S = x^ w^T [B, C]; small C, tests, compat mode) ------- */
 

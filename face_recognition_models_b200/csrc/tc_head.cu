@@ -17,13 +17,14 @@
 // (48 KB each), two 256-column TMEM accumulators so the epilogue of tile t overlaps the MMAs of t+1.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 #include <map>
 #include <tuple>
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, MAX_STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64, MAX_STAGES = 6;
 constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
 // Output staging for coalesced global stores (BWD_G: bf16 G rows, DW: fp32 dw^ rows): per epilogue warp
 // 32 rows x 256 B (+16 B pad per row against bank conflicts).  Those two modes run 3 pipeline stages.
@@ -35,17 +36,26 @@ constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 
 enum { MODE_FWD = 0, MODE_BWD_G = 1, MODE_DX = 2, MODE_DW = 3, MODE_DWF = 4 };
+// Per-mode pipeline configuration.  cta2 = the cta_group::2 variant: a cluster of two CTAs (one SM pair) computes a
+// 256-row tile; each CTA keeps its own 128 A rows + 128 accumulator lanes and loads only HALF of the B tile, the
+// tensor cores of both SMs read both halves.  Per-CTA bytes per MMA drop by a third to a half (the 1-CTA kernels
+// were bound by per-SM TMA/L2 request throughput), which also buys deeper pipelines.
 constexpr bool mode_stages_out(int mode) { return mode == MODE_BWD_G || mode == MODE_DW || mode == MODE_DWF; }
 constexpr int mode_bn(int mode) { return mode == MODE_DX ? 512 : 256; }          // accumulator columns per tile
 constexpr int mode_nbuf(int mode) { return mode == MODE_DX ? 1 : 2; }            // TMEM accumulators in flight
-constexpr int mode_stages(int mode) { return mode == MODE_DX ? 2 : (mode_stages_out(mode) ? 3 : 4); }
-constexpr int mode_stage_bytes(int mode) { return A_STAGE_BYTES + mode_bn(mode) * BK * 2; }
-constexpr int mode_smem_bytes(int mode) {
-  return mode_stages(mode) * mode_stage_bytes(mode) + 1024 /*align slack*/ + 256 /*barriers*/ +
+constexpr int mode_stage_bytes(int mode, bool cta2) { return A_STAGE_BYTES + (mode_bn(mode) / (cta2 ? 2 : 1)) * BK * 2; }
+constexpr int mode_stages(int mode, bool cta2) {
+  if (cta2) return mode == MODE_FWD ? 6 : 4;
+  return mode == MODE_DX ? 2 : (mode_stages_out(mode) ? 3 : 4);
+}
+constexpr int mode_smem_bytes(int mode, bool cta2) {
+  return mode_stages(mode, cta2) * mode_stage_bytes(mode, cta2) + 1024 /*align slack*/ + 256 /*barriers*/ +
          (mode_stages_out(mode) ? 8 * STG_WARP_BYTES : 0);
 }
-static_assert(mode_smem_bytes(MODE_BWD_G) <= 232448 && mode_smem_bytes(MODE_FWD) <= 232448 &&
-              mode_smem_bytes(MODE_DX) <= 232448, "smem budget");
+static_assert(mode_smem_bytes(MODE_BWD_G, false) <= 232448 && mode_smem_bytes(MODE_FWD, false) <= 232448 &&
+              mode_smem_bytes(MODE_DX, false) <= 232448 && mode_smem_bytes(MODE_BWD_G, true) <= 232448 &&
+              mode_smem_bytes(MODE_FWD, true) <= 232448 && mode_smem_bytes(MODE_DX, true) <= 232448 &&
+              mode_smem_bytes(MODE_DWF, true) <= 232448, "smem budget");
 
 struct TcArgs {
   int m_tiles, n_tiles, n_split, k_blocks_total, k_blocks_per_split;
@@ -107,6 +117,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a TMA box (no shared memory, no barrier): hides HBM latency beyond the smem pipeline depth.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -149,6 +165,57 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// ---- cta_group::2 (SM pair) variants -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank)
+      : "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes land on the LEADER CTA's mbarrier
+// (peer bit 24 of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100): start addr [0,14) >>4, LBO [16,30) >>4, SBO [32,46) >>4,
 // version=1 at [46,48), layout type [61,64) (2 = SWIZZLE_128B).
@@ -184,22 +251,24 @@ struct Work {
   int n_tile;        // FWD: class-tile index
 };
 
-template <int MODE>
-__device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t) {
+// Tile -> work.  BMT = rows of the (pair) tile: 128, or 256 with cta_group::2; `rank` selects this CTA's 128 rows.
+template <int MODE, bool CTA2>
+__device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t, int rank) {
+  constexpr int BMT = CTA2 ? 2 * BM : BM;
   Work w;
   w.split = 0;
   w.n_tile = 0;
   if (MODE == MODE_FWD || MODE == MODE_BWD_G) {
     int m = (int)(t % a.m_tiles), n = (int)(t / a.m_tiles);
-    w.m0 = m * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK; w.n_tile = n;
+    w.m0 = m * BMT + rank * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK; w.n_tile = n;
   } else if (MODE == MODE_DX) {
     w.split = (int)(t / a.m_tiles);
-    w.m0 = (int)(t % a.m_tiles) * BM;
+    w.m0 = (int)(t % a.m_tiles) * BMT + rank * BM;
     w.n0 = 0;
     w.kb0 = w.split * a.k_blocks_per_split;
     w.kb1 = min(a.k_blocks_total, w.kb0 + a.k_blocks_per_split);
   } else {
-    w.m0 = (int)(t >> 1) * BM;
+    w.m0 = (int)(t >> 1) * BMT + rank * BM;
     w.n0 = (int)(t & 1) * BN;
     w.kb0 = 0; w.kb1 = a.k_blocks_total;
   }
@@ -366,11 +435,16 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int
   }
 }
 
-template <int MODE, int V>
+template <int MODE, int V, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  constexpr int STAGES = mode_stages(MODE);
-  constexpr int STAGE_BYTES = mode_stage_bytes(MODE);
+  constexpr int STAGES = mode_stages(MODE, CTA2);
+  constexpr int STAGE_BYTES = mode_stage_bytes(MODE, CTA2);
+  constexpr int NCTA = CTA2 ? 2 : 1;
+  constexpr int GW = BN / NCTA;                      // B columns (of one 256-wide UMMA group) held by this CTA
+  const int rank = CTA2 ? (int)cluster_ctarank() : 0;
+  const int64_t pid = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;        // tile-scheduling unit: CTA or CTA pair
+  const int64_t npid = CTA2 ? (gridDim.x >> 1) : gridDim.x;
   constexpr int BNT = mode_bn(MODE);                 // accumulator columns of one tile (256, DX: 512)
   constexpr int NBUF = mode_nbuf(MODE);
   constexpr bool IS_DW = (MODE == MODE_DW || MODE == MODE_DWF);
@@ -392,18 +466,20 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, NCTA);                // pair: leader's expect_tx arrive + the peer producer's arrive
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS);     // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS * NCTA);   // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS); else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -411,43 +487,55 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr bool B_MN = (MODE == MODE_DX || IS_DW);
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
+    // =============================== TMA producer (both CTAs of a pair) ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        const Work w = get_work<MODE>(a, t);
+      for (int64_t t = pid; t < a.total_tiles; t += npid) {
+        const Work w = get_work<MODE, CTA2>(a, t, rank);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = tiles_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
           const uint32_t fb = bar_full + 8 * stage;
-          mbar_expect_tx(fb, STAGE_BYTES);
+          if (!CTA2) {
+            mbar_expect_tx(fb, STAGE_BYTES);
+          } else if (rank == 0) {
+            mbar_expect_tx(fb, 2 * STAGE_BYTES);                            // bytes of both CTAs land on the leader's barrier
+          } else {
+            mbar_arrive_cluster(fb, 0);
+          }
+          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+            if (CTA2) tma_load_2d_2sm(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &tmA, fb, kb * BK, w.m0);                       // box [64 k][128 rows]
+            load(sa, &tmA, kb * BK, w.m0);                                  // box [64 k][128 rows]
           } else {
 #pragma unroll
-            for (int bx = 0; bx < BM / 64; ++bx) tma_load_2d(sa + bx * 8192, &tmA, fb, w.m0 + 64 * bx, kb * BK);
+            for (int bx = 0; bx < BM / 64; ++bx) load(sa + bx * 8192, &tmA, w.m0 + 64 * bx, kb * BK);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, fb, kb * BK, w.n0);                       // box [64 k][256 rows]
+            load(sb, &tmB, kb * BK, w.n0 + rank * GW);                      // box [64 k][GW rows]
           } else {
 #pragma unroll
-            for (int bx = 0; bx < BNT / 64; ++bx) tma_load_2d(sb + bx * 8192, &tmB, fb, w.n0 + 64 * bx, kb * BK);
+            for (int nh = 0; nh < BNT / BN; ++nh)
+#pragma unroll
+              for (int bx = 0; bx < GW / 64; ++bx)
+                load(sb + (nh * (GW / 64) + bx) * 8192, &tmB, w.n0 + nh * BN + rank * GW + 64 * bx, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BM, BN);
+    // =============================== MMA issuer (leader CTA only) ===============================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BM * NCTA, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
-      for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
-        const Work w = get_work<MODE>(a, t);
+      for (int64_t t = pid; t < a.total_tiles; t += npid, ++it) {
+        const Work w = get_work<MODE, CTA2>(a, t, rank);
         const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
-        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);                       // epilogue drained this accumulator
+        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);                       // epilogue(s) drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
@@ -460,16 +548,19 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint64_t da = A_MN ? desc_mnmajor(sa, k) : desc_kmajor(sa, k);
             const uint32_t acc = (kb > w.kb0 || k > 0) ? 1u : 0u;
 #pragma unroll
-            for (int nh = 0; nh < BNT / BN; ++nh) {                       // DX: two N=256 halves of the 512-wide tile
-              const uint32_t sbh = sb + nh * (BN / 64) * 8192;
+            for (int nh = 0; nh < BNT / BN; ++nh) {                       // DX: two N=256 groups of the 512-wide tile
+              const uint32_t sbh = sb + nh * (GW / 64) * 8192;
               const uint64_t db = B_MN ? desc_mnmajor(sbh, k) : desc_kmajor(sbh, k);
-              umma_bf16(tmem_d + nh * BN, da, db, idesc, acc);
+              if (CTA2) umma_bf16_2sm(tmem_d + nh * BN, da, db, idesc, acc);
+              else umma_bf16(tmem_d + nh * BN, da, db, idesc, acc);
             }
           }
-          umma_commit(bar_empty + 8 * stage);                              // frees the smem stage when MMAs retire
+          // frees the smem stage (in both CTAs) when the MMAs retire
+          if (CTA2) umma_commit_2sm(bar_empty + 8 * stage); else umma_commit(bar_empty + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * buf);                                  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue(s)
+        if (CTA2) umma_commit_2sm(bar_tfull + 8 * buf); else umma_commit(bar_tfull + 8 * buf);
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -483,8 +574,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const float ha = (V == V_CURR) ? a.state[4] : p.hard_a;
     const float hb = p.hard_b, lo = p.lo, hi = p.hi;
     uint32_t it = 0;
-    for (int64_t t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
-      const Work w = get_work<MODE>(a, t);
+    for (int64_t t = pid; t < a.total_tiles; t += npid, ++it) {
+      const Work w = get_work<MODE, CTA2>(a, t, rank);
       const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
       const int64_t row = (int64_t)w.m0 + r;
       RowCtx rc;
@@ -608,7 +699,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(bar_tempty + 8 * buf, 0); else mbar_arrive(bar_tempty + 8 * buf);
+      }
       if (MODE == MODE_BWD_G) {
         // staged [32 rows][128 bf16 = 256 B] -> global, full lines: 16 lanes per row, 2 rows per instruction
         __nv_bfloat16* obase = a.G + ((int64_t)w.m0 + q * 32) * a.C_pad + w.n0 + cbase;
@@ -631,10 +724,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: the peer's smem / TMEM stay valid until both are done
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTA2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -682,17 +775,45 @@ int num_sms() {
   return n;
 }
 
-template <int MODE, int V>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
+// cta_group::2 is the default; MH_TC_CTA2=0 selects the single-CTA kernels (kept for A/B measurements).
+bool use_cta2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MH_TC_CTA2");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int MODE, int V, bool CTA2>
+int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
   static bool attr_set = false;
+  constexpr int smem = mode_smem_bytes(MODE, CTA2);
   if (!attr_set) {
-    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, mode_smem_bytes(MODE)));
+    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  int grid = (int)std::min<int64_t>(args.total_tiles, num_sms());
-  tc_kernel<MODE, V><<<grid, NUM_THREADS, mode_smem_bytes(MODE), st>>>(ta, tb, args);
-  MH_LAUNCH_OK();
+  const int units = CTA2 ? num_sms() / 2 : num_sms();
+  const int n = (int)std::min<int64_t>(args.total_tiles, units);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CTA2 ? 2 * n : n);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel<MODE, V, CTA2>, ta, tb, args));
   return MH_OK;
+}
+
+template <int MODE, int V>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, bool cta2, cudaStream_t st) {
+  return cta2 ? launch_impl<MODE, V, true>(ta, tb, args, st) : launch_impl<MODE, V, false>(ta, tb, args, st);
 }
 
 int variant_of(const MhParams& p) {
@@ -704,13 +825,13 @@ int variant_of(const MhParams& p) {
 }
 
 template <int MODE>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, bool cta2, cudaStream_t st) {
   switch (variant_of(args.p)) {
-    case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, st);
-    case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, st);
-    case V_SPHERE: return launch<MODE, V_SPHERE>(ta, tb, args, st);
-    case V_MV: return launch<MODE, V_MV>(ta, tb, args, st);
-    default: return launch<MODE, V_CURR>(ta, tb, args, st);
+    case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, cta2, st);
+    case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, cta2, st);
+    case V_SPHERE: return launch<MODE, V_SPHERE>(ta, tb, args, cta2, st);
+    case V_MV: return launch<MODE, V_MV>(ta, tb, args, cta2, st);
+    default: return launch<MODE, V_CURR>(ta, tb, args, cta2, st);
   }
 }
 
@@ -732,17 +853,19 @@ extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, 
   MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && stats_tiles, "null pointer");
   if (int e = check_common(B, B_pad, C, C_pad)) return e;
   MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
+  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
+  const int bmt = cta2 ? 2 * BM : BM;
   CUtensorMap ta, tb;
   if (int e = make_tmap(&ta, x_hat_bf16, B_pad, MH_D, BM)) return e;
-  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN)) return e;
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, cta2 ? BN / 2 : BN)) return e;
   TcArgs a{};
-  a.m_tiles = (int)(B_pad / BM); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
+  a.m_tiles = (int)(B_pad / bmt); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
   a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
   a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
   a.p = mh_make_params(cfg_host);
   a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
   a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.stats_tiles = stats_tiles;
-  return launch_variant<MODE_FWD>(ta, tb, a, (cudaStream_t)stream);
+  return launch_variant<MODE_FWD>(ta, tb, a, cta2, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
@@ -752,11 +875,13 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
   MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && lse2 && G_bf16, "null pointer");
   if (int e = check_common(B, B_pad, C, C_pad)) return e;
   MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
+  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
+  const int bmt = cta2 ? 2 * BM : BM;
   CUtensorMap ta, tb;
   if (int e = make_tmap(&ta, x_hat_bf16, B_pad, MH_D, BM)) return e;
-  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN)) return e;
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, cta2 ? BN / 2 : BN)) return e;
   TcArgs a{};
-  a.m_tiles = (int)(B_pad / BM); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
+  a.m_tiles = (int)(B_pad / bmt); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
   a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
   a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
   a.p = mh_make_params(cfg_host);
@@ -765,15 +890,16 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
   a.G = (__nv_bfloat16*)G_bf16;
   a.rsum = r_colsum;
   if (r_colsum) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
-  return launch_variant<MODE_BWD_G>(ta, tb, a, (cudaStream_t)stream);
+  return launch_variant<MODE_BWD_G>(ta, tb, a, cta2, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
                                  int* n_split_host, void* stream) {
   MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
-  const int m_tiles = (int)(B_pad / BM);
+  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
+  const int m_tiles = (int)(B_pad / (cta2 ? 2 * BM : BM));
   const int kb_total = (int)(C_pad / BK);
-  int n_split = std::max(1, num_sms() / m_tiles);
+  int n_split = std::max(1, (cta2 ? num_sms() / 2 : num_sms()) / m_tiles);
   n_split = std::min(n_split, kb_total);
   int per = (kb_total + n_split - 1) / n_split;
   n_split = (kb_total + per - 1) / per;                 // no empty splits
@@ -789,7 +915,7 @@ extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pa
   a.total_tiles = (int64_t)m_tiles * n_split;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
-  return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
+  return launch<MODE_DX, V_NONE>(ta, tb, a, cta2, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
@@ -799,13 +925,14 @@ extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pa
   CUtensorMap ta, tb;
   if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, 64)) return e;          // A = G^T, MN-major boxes [64 rows][64 cls]
   if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;       // B = x^,  MN-major boxes [64 rows][64 d]
+  const bool cta2 = use_cta2();                                     // C_pad is always a multiple of 256
   TcArgs a{};
-  a.m_tiles = (int)(C_pad / BM); a.n_tiles = 2; a.n_split = 1;
+  a.m_tiles = (int)(C_pad / (cta2 ? 2 * BM : BM)); a.n_tiles = 2; a.n_split = 1;
   a.k_blocks_total = (int)(B_pad / BK); a.k_blocks_per_split = a.k_blocks_total;
   a.total_tiles = (int64_t)a.m_tiles * 2;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = dw_hat; a.out_split_stride = 0;
-  return launch<MODE_DW, V_NONE>(ta, tb, a, (cudaStream_t)stream);
+  return launch<MODE_DW, V_NONE>(ta, tb, a, cta2, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
@@ -818,13 +945,14 @@ extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_
   CUtensorMap ta, tb;
   if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, 64)) return e;
   if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;
+  const bool cta2 = use_cta2();
   TcArgs a{};
-  a.m_tiles = (int)(C_pad / BM); a.n_tiles = 2; a.n_split = 1;
+  a.m_tiles = (int)(C_pad / (cta2 ? 2 * BM : BM)); a.n_tiles = 2; a.n_split = 1;
   a.k_blocks_total = (int)(B_pad / BK); a.k_blocks_per_split = a.k_blocks_total;
   a.total_tiles = (int64_t)a.m_tiles * 2;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C;
   a.out = dW; a.out_split_stride = 0;
   a.rsum = const_cast<float*>(r_colsum); a.w_hat = (const __nv_bfloat16*)w_hat_bf16; a.inv_norm = inv_norm;
   a.gscal = gscal; a.layout = layout; a.ld = ld;
-  return launch<MODE_DWF, V_NONE>(ta, tb, a, (cudaStream_t)stream);
+  return launch<MODE_DWF, V_NONE>(ta, tb, a, cta2, (cudaStream_t)stream);
 }

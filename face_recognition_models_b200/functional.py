@@ -105,7 +105,7 @@ class HeadEngine:
         dev = x.device
         B = x.shape[0]
         Cn = self.C
-        B_pad = _round_up(B, L.TILE)
+        B_pad = _round_up(B, 2 * L.TILE)     # 256: one cta_group::2 pair tile of rows
         C_pad = _round_up(Cn, L.NTILE)
         ld = W.shape[1]
         if self.layout == L.LAYOUT_CD:

@@ -5,7 +5,7 @@
 //   FWD    S = x^ w^T tile  -> clamp/margin/scale -> online max/sum-exp + rank count per row.
 //          Nothing of size B x C is written (replaces criterion.py:267-301 & siblings +
 //          nn.CrossEntropyLoss, model_utils.py:179, + accuracy, metrics.py:3-16).
-//   BWD_G  recompute the S tile -> G = (P - Y) * dz/dcos as bf16 [B_pad, C_pad].
+//   BWD_G  recompute the S tile -> G = (P - Y) * dz/dcos as bf16, class-tiled [C_pad/128][B_pad][128].
 //          Also accumulates r_j = sum_i G_ij * cos_ij (= w^_j . dw^_j), the normalise-backward projection.
 //   DX     dx^ partials = G . w^      (A = G K-major,  B = w^ MN-major, split over classes; one 128 x 512
 //          accumulator = all 512 TMEM columns per CTA, so every G byte is read by exactly one CTA)
@@ -507,11 +507,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
             if (CTA2) tma_load_2d_2sm(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
           };
-          if (!A_MN) {
+          if (MODE == MODE_DX) {
+            // A = G, class-tiled [C_pad/128][B_pad][128]: k-block kb = classes 64kb.. -> slab kb/2, columns (kb&1)*64
+            load(sa, &tmA, (kb & 1) * 64, (kb >> 1) * (int)a.B_pad + w.m0);  // box [64 k][128 rows]
+          } else if (!A_MN) {
             load(sa, &tmA, kb * BK, w.m0);                                  // box [64 k][128 rows]
           } else {
+            // A = G^T from the class-tiled G: this CTA's 128 classes are slab m0/128; box [64 classes][64 rows]
 #pragma unroll
-            for (int bx = 0; bx < BM / 64; ++bx) load(sa + bx * 8192, &tmA, w.m0 + 64 * bx, kb * BK);
+            for (int bx = 0; bx < BM / 64; ++bx)
+              load(sa + bx * 8192, &tmA, 64 * bx, (w.m0 / 128) * (int)a.B_pad + kb * BK);
           }
           if (!B_MN) {
             load(sb, &tmB, kb * BK, w.n0 + rank * GW);                      // box [64 k][GW rows]
@@ -704,12 +709,14 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       if (MODE == MODE_BWD_G) {
         // staged [32 rows][128 bf16 = 256 B] -> global, full lines: 16 lanes per row, 2 rows per instruction
-        __nv_bfloat16* obase = a.G + ((int64_t)w.m0 + q * 32) * a.C_pad + w.n0 + cbase;
+        // G is stored class-tiled: [C_pad/128][B_pad][128] (a 128-class slab of all rows is contiguous), so the dW
+        // GEMM reads one contiguous 256 KB block per class tile and this warp's 32 rows are 8 KB contiguous.
+        __nv_bfloat16* obase = a.G + (((int64_t)(w.n0 + cbase) / 128) * a.B_pad + w.m0 + q * 32) * 128;
 #pragma unroll
         for (int i2 = 0; i2 < 16; ++i2) {
           const int rr = 2 * i2 + (lane >> 4);
           const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * STG_ROW_BYTES + (lane & 15) * 16);
-          *reinterpret_cast<uint4*>(obase + (int64_t)rr * a.C_pad + (lane & 15) * 8) = val;
+          *reinterpret_cast<uint4*>(obase + (int64_t)rr * 128 + (lane & 15) * 8) = val;
         }
         __syncwarp();
       }
@@ -843,7 +850,7 @@ extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { return 2 * ((C_pad + BN - 1
 static int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
   MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % BM == 0, "B_pad must be a multiple of 128");
   MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % BN == 0, "C_pad must be a multiple of 256 for the tensor-core path");
-  MH_CHECK_ARG(C_pad < (1ll << 31) && B_pad < (1ll << 31), "dimension too large");
+  MH_CHECK_ARG(C_pad < (1ll << 31) && B_pad < (1ll << 31) && (C_pad / 128) * B_pad < (1ll << 31), "dimension too large");
   return MH_OK;
 }
 
@@ -907,7 +914,7 @@ extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pa
   if (!out) return MH_OK;
   MH_CHECK_ARG(G_bf16 && w_hat_bf16, "null pointer");
   CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, BM)) return e;          // A = G, K-major (K = class)
+  if (int e = make_tmap(&ta, G_bf16, (C_pad / 128) * B_pad, 128, BM)) return e;   // A = G (class-tiled), K-major
   if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, 64)) return e;       // B = w^, MN-major boxes [64 k][64 d]
   TcArgs a{};
   a.m_tiles = m_tiles; a.n_tiles = 1; a.n_split = n_split;
@@ -923,7 +930,7 @@ extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pa
   MH_CHECK_ARG(G_bf16 && x_hat_bf16 && dw_hat, "null pointer");
   MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
   CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, 64)) return e;          // A = G^T, MN-major boxes [64 rows][64 cls]
+  if (int e = make_tmap(&ta, G_bf16, (C_pad / 128) * B_pad, 128, 64)) return e;    // A = G^T (class-tiled G), MN-major boxes
   if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;       // B = x^,  MN-major boxes [64 rows][64 d]
   const bool cta2 = use_cta2();                                     // C_pad is always a multiple of 256
   TcArgs a{};
@@ -943,7 +950,7 @@ extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_
   MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
   MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)dW & 15) == 0), "CD dW must be 16-byte aligned");
   CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, G_bf16, B_pad, C_pad, 64)) return e;
+  if (int e = make_tmap(&ta, G_bf16, (C_pad / 128) * B_pad, 128, 64)) return e;    // class-tiled G
   if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;
   const bool cta2 = use_cta2();
   TcArgs a{};

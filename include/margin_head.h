@@ -153,8 +153,10 @@ int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, 
                   const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                   const int32_t* label_local, const float* state, float* stats_tiles, void* stream);
 
-/* Backward step 1: recompute the logit tiles and write G = (P - Y) * dz/dcos as bf16 [B_pad, C_pad]
- * (the only B x C object of the path; never the logits).  lse2 = rowout plane MH_RO_LSE2.
+/* Backward step 1: recompute the logit tiles and write G = (P - Y) * dz/dcos as bf16 (the only B x C object of the
+ * path; never the logits).  G is stored CLASS-TILED: [C_pad/128][B_pad][128], i.e. element (row i, class j) lives at
+ * ((j/128)*B_pad + i)*128 + j%128, so each 128-class slab of all rows is one contiguous block (DRAM-page friendly for
+ * both consumers); mh_tc_backward_dx / _dw / _dw_fused expect this layout.  lse2 = rowout plane MH_RO_LSE2.
  * r_colsum [C_pad] (may be NULL) receives r_j = sum_i G_ij * cos_ij = w^_j . dw^_j, the projection term of
  * the normalise-backward of W; it is zeroed (stream-ordered) before the kernel accumulates into it. */
 int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,

@@ -158,18 +158,20 @@ def stage_tcgemm():
         G = (torch.randn(B_pad, C_pad, device=dev) * 0.5).to(torch.bfloat16)
         wh = (torch.randn(C_pad, 512, device=dev) * 0.1).to(torch.bfloat16)
         xh = (torch.randn(B_pad, 512, device=dev) * 0.1).to(torch.bfloat16)
+        Gl = G                                                       # logical [B_pad, C_pad]
+        G = G.view(B_pad, C_pad // 128, 128).permute(1, 0, 2).contiguous()   # class-tiled storage the kernels expect
         ns = C.c_int(0)
         L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(wh), C.c_void_p(0), C.byref(ns), _stream())
         part = torch.zeros(ns.value, B_pad, 512, device=dev)
         L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(wh), _ptr(part), C.byref(ns), _stream())
         torch.cuda.synchronize()
         got = part.sum(0)
-        ref = G.double() @ wh.double()
+        ref = Gl.double() @ wh.double()
         print(f"tc dx  B_pad={B_pad} C_pad={C_pad} n_split={ns.value} rel={rel(got, ref):.3e}")
         dw = torch.zeros(C_pad, 512, device=dev)
         L.call("mh_tc_backward_dw", _ptr(G), B_pad, C_pad, _ptr(xh), _ptr(dw), _stream())
         torch.cuda.synchronize()
-        refw = G.double().t() @ xh.double()
+        refw = Gl.double().t() @ xh.double()
         print(f"tc dw  B_pad={B_pad} C_pad={C_pad} rel={rel(dw, refw):.3e}")
         assert rel(got, ref) < 1e-3 and rel(dw, refw) < 1e-3
 

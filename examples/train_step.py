@@ -1,0 +1,77 @@
+"""Reference-style training step with the B200 head as a drop-in (BASELINE configs 1 and 5).
+
+    python examples/train_step.py --steps 5                                   # 1 GPU, ArcFace, C=10,575
+    torchrun --nproc-per-node 8 examples/train_step.py --classes 2000000      # DDP backbone + class-sharded head
+
+Mirrors main_code/utils/model_utils.py:168-192 (autocast backbone, GradScaler, SGD momentum 0.9 / wd 5e-4,
+loss.item() every step) with the three-line change of INTEGRATION.md: the loss and the top-1/5 accuracies
+come from head.fused_loss instead of materialised logits.  Synthetic 112x112 faces, random-init ResNet-50.
+"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torchvision
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import face_recognition_models_b200 as pkg  # noqa: E402
+
+
+def build_backbone(name="resnet50"):
+    net = getattr(torchvision.models, name)(weights=None)          # backbones.py:13-18 without the download
+    net.fc = nn.Linear(net.fc.in_features, 512)
+    return net
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--classes", type=int, default=10575)
+    ap.add_argument("--backbone", default="resnet50")
+    ap.add_argument("--lambda_g", type=float, default=0.0)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1 + rank)
+    backbone = build_backbone(a.backbone).to(dev)
+    if world > 1:
+        backbone = nn.parallel.DistributedDataParallel(backbone, device_ids=[local])
+        head = pkg.ShardedMarginHead("arcface", a.classes, s=64.0, m=0.5, easy_margin=False, dx_scale=world).to(dev)
+        head_params = [head.shard_parameter()]
+    else:
+        head = pkg.ArcFace(512, a.classes, s=64.0, m=0.5, easy_margin=False).to(dev)
+        head_params = list(head.parameters())
+    opt = torch.optim.SGD(list(backbone.parameters()) + head_params, lr=0.1, momentum=0.9, weight_decay=5e-4)
+    scaler = torch.amp.GradScaler("cuda")
+    images = torch.randn(a.batch, 3, 112, 112, device=dev)
+    target = torch.randint(0, a.classes, (a.batch,), device=dev)
+    for step in range(a.steps):
+        t0 = time.time()
+        with torch.autocast("cuda"):
+            feats = backbone(images)                                   # fp16 features, as under the reference's autocast
+        out = head.fused_loss(feats, target)
+        loss = out.loss + a.lambda_g * out.loss_g
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        lv = loss.item()
+        if rank == 0:
+            print(f"step {step}: loss {lv:.4f} acc@1 {float(out.acc1):.2f} acc@5 {float(out.acc5):.2f} "
+                  f"({a.batch * world / (time.time() - t0):.1f} img/s)")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

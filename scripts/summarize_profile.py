@@ -17,6 +17,11 @@ NAMES = {
 
 
 def api_name(kernel):
+    import re
+    m = re.search(r"tc_kernel<\(?(?:int\))?(\d)", kernel)
+    if m:
+        return ["mh_tc_forward", "mh_tc_backward_g", "mh_tc_backward_dx", "mh_tc_backward_dw",
+                "mh_tc_backward_dw_fused"][int(m.group(1))]
     for k, v in NAMES.items():
         if k in kernel:
             return v

@@ -66,7 +66,7 @@ SIGNATURES = {
     "mh_norm_backward_w": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
 }
 _RESTYPES = {"mh_version": C.c_char_p, "mh_last_error": C.c_char_p, "mh_fwd_num_tiles": C.c_int64}
-EXPORTED = sorted(list(SIGNATURES) + ["mh_version", "mh_last_error", "mh_fwd_num_tiles"])
+EXPORTED = sorted(list(SIGNATURES) + ["mh_version", "mh_last_error", "mh_fwd_num_tiles", "mh_tc_schedule_tiles"])
 
 
 class MarginHeadError(RuntimeError):
@@ -93,6 +93,8 @@ def load() -> C.CDLL:
     lib.mh_last_error.argtypes = []
     lib.mh_fwd_num_tiles.restype = C.c_int64
     lib.mh_fwd_num_tiles.argtypes = [C.c_int64]
+    lib.mh_tc_schedule_tiles.restype = C.c_int64
+    lib.mh_tc_schedule_tiles.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64]
     _lib = lib
     return lib
 

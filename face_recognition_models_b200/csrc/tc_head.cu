@@ -26,10 +26,6 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, MAX_STAGES = 6;
 constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
-// Output staging for coalesced global stores (BWD_G: bf16 G rows, DW: fp32 dw^ rows): per epilogue warp
-// 32 rows x 256 B (+16 B pad per row against bank conflicts).  Those two modes run 3 pipeline stages.
-constexpr int STG_ROW_BYTES = 256 + 16;
-constexpr int STG_WARP_BYTES = 32 * STG_ROW_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
@@ -40,26 +36,42 @@ enum { MODE_FWD = 0, MODE_BWD_G = 1, MODE_DX = 2, MODE_DW = 3, MODE_DWF = 4 };
 // 256-row tile; each CTA keeps its own 128 A rows + 128 accumulator lanes and loads only HALF of the B tile, the
 // tensor cores of both SMs read both halves.  Per-CTA bytes per MMA drop by a third to a half (the 1-CTA kernels
 // were bound by per-SM TMA/L2 request throughput), which also buys deeper pipelines.
-constexpr bool mode_stages_out(int mode) { return mode == MODE_BWD_G || mode == MODE_DW || mode == MODE_DWF; }
+//
+// A-stationary (cta2 FWD / BWD_G): the pair's x^ tile (128 rows x 512 per CTA = 128 KB) stays resident in shared
+// memory while the pair sweeps class tiles, so only w^ streams (16 KB per CTA per k-block): L2 -> SM traffic per
+// tile halves (64 -> 32 B/clk/SM; the non-stationary kernels sat on the ~6.3 KB/clk chip-wide L2 delivery cap).
+constexpr bool mode_astat(int mode, bool cta2) { return cta2 && (mode == MODE_FWD || mode == MODE_BWD_G); }
+constexpr int A_RESIDENT_BYTES = BM * MH_D * 2;                                   // 128 KB
+// Output staging for coalesced global stores, per epilogue warp:
+//   BWD_G: 32 rows x 128 B (64 bf16 columns), XOR-swizzled 16 B pieces, flushed every two 32-column chunks;
+//   DW/DWF: 32 rows x 256 B (+16 B pad per row), fp32 dw^ rows.
+constexpr int STG_ROW_BYTES = 256 + 16;
+constexpr int mode_stg_warp_bytes(int mode) {
+  return mode == MODE_BWD_G ? 32 * 128 : ((mode == MODE_DW || mode == MODE_DWF) ? 32 * STG_ROW_BYTES : 0);
+}
 constexpr int mode_bn(int mode) { return mode == MODE_DX ? 512 : 256; }          // accumulator columns per tile
 constexpr int mode_nbuf(int mode) { return mode == MODE_DX ? 1 : 2; }            // TMEM accumulators in flight
-constexpr int mode_stage_bytes(int mode, bool cta2) { return A_STAGE_BYTES + (mode_bn(mode) / (cta2 ? 2 : 1)) * BK * 2; }
+constexpr int mode_stage_bytes(int mode, bool cta2) {
+  return (mode_astat(mode, cta2) ? 0 : A_STAGE_BYTES) + (mode_bn(mode) / (cta2 ? 2 : 1)) * BK * 2;
+}
 constexpr int mode_stages(int mode, bool cta2) {
-  if (cta2) return mode == MODE_FWD ? 6 : 4;
-  return mode == MODE_DX ? 2 : (mode_stages_out(mode) ? 3 : 4);
+  if (mode_astat(mode, cta2)) return mode == MODE_FWD ? 6 : 4;
+  if (cta2) return 4;
+  return mode == MODE_DX ? 2 : (mode_stg_warp_bytes(mode) ? 3 : 4);
 }
 constexpr int mode_smem_bytes(int mode, bool cta2) {
-  return mode_stages(mode, cta2) * mode_stage_bytes(mode, cta2) + 1024 /*align slack*/ + 256 /*barriers*/ +
-         (mode_stages_out(mode) ? 8 * STG_WARP_BYTES : 0);
+  return (mode_astat(mode, cta2) ? A_RESIDENT_BYTES : 0) + mode_stages(mode, cta2) * mode_stage_bytes(mode, cta2) +
+         1024 /*align slack*/ + 256 /*barriers*/ + NUM_EPI_WARPS * mode_stg_warp_bytes(mode);
 }
 static_assert(mode_smem_bytes(MODE_BWD_G, false) <= 232448 && mode_smem_bytes(MODE_FWD, false) <= 232448 &&
               mode_smem_bytes(MODE_DX, false) <= 232448 && mode_smem_bytes(MODE_BWD_G, true) <= 232448 &&
               mode_smem_bytes(MODE_FWD, true) <= 232448 && mode_smem_bytes(MODE_DX, true) <= 232448 &&
-              mode_smem_bytes(MODE_DWF, true) <= 232448, "smem budget");
+              mode_smem_bytes(MODE_DWF, true) <= 232448 && mode_smem_bytes(MODE_DWF, false) <= 232448, "smem budget");
 
 struct TcArgs {
   int m_tiles, n_tiles, n_split, k_blocks_total, k_blocks_per_split;
   int64_t total_tiles;
+  int sG, sE, n_fixed;         // A-stationary schedule (see StatIter)
   MhParams p;
   int64_t B, C, B_pad, C_pad;
   const float* rowp;
@@ -249,6 +261,7 @@ struct Work {
   int kb0, kb1;      // k-block range
   int split;         // DX split index
   int n_tile;        // FWD: class-tile index
+  int m_tile;        // A-stationary modes: row-tile index (the resident x^ tile)
 };
 
 // Tile -> work.  BMT = rows of the (pair) tile: 128, or 256 with cta_group::2; `rank` selects this CTA's 128 rows.
@@ -258,6 +271,7 @@ __device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t, int rank) {
   Work w;
   w.split = 0;
   w.n_tile = 0;
+  w.m_tile = 0;
   if (MODE == MODE_FWD || MODE == MODE_BWD_G) {
     int m = (int)(t % a.m_tiles), n = (int)(t / a.m_tiles);
     w.m0 = m * BMT + rank * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK; w.n_tile = n;
@@ -274,6 +288,66 @@ __device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t, int rank) {
   }
   return w;
 }
+
+// A-stationary tile schedule (cta2 FWD / BWD_G).  `units` CTA pairs, m_tiles <= units row tiles of 256 rows:
+//   * sG = units / m_tiles pairs are bound to each row tile m; pair q of the group takes class tiles q, q+sG, ... of
+//     [0, n_fixed).  The groups of all row tiles sweep the classes in lockstep, so a w^ tile fetched from HBM by one
+//     row tile is an L2 hit for the others.
+//   * the sE = units - sG*m_tiles left-over pairs share the class tiles [n_fixed, n_tiles) of ALL row tiles, each taking
+//     a contiguous chunk in (m-major, n-minor) order (they reload x^ when m changes); n_fixed balances both kinds.
+struct StatIter {
+  int fixed, m, n, step, n_end, u, u_end, n_ext, n_fixed;
+  __host__ __device__ __forceinline__ void init(const TcArgs& a, int pid) {
+    const int nfix_pairs = a.sG * a.m_tiles;
+    fixed = pid < nfix_pairs;
+    m = n = step = n_end = u = u_end = 0;
+    n_fixed = a.n_fixed;
+    n_ext = a.n_tiles - a.n_fixed;
+    if (fixed) {
+      m = pid % a.m_tiles; n = pid / a.m_tiles; step = a.sG; n_end = a.n_fixed;
+    } else if (a.sE > 0 && n_ext > 0) {
+      const int e = pid - nfix_pairs;
+      const int64_t U = (int64_t)n_ext * a.m_tiles;
+      u = (int)(U * e / a.sE);
+      u_end = (int)(U * (e + 1) / a.sE);
+    }
+  }
+  __host__ __device__ __forceinline__ bool next(int& m_out, int& n_out) {
+    if (fixed) {
+      if (n >= n_end) return false;
+      m_out = m; n_out = n; n += step;
+      return true;
+    }
+    if (u >= u_end) return false;
+    m_out = u / n_ext; n_out = n_fixed + u % n_ext; ++u;
+    return true;
+  }
+};
+
+// The tile sequence of one CTA (pair); the producer, MMA and epilogue roles all walk the same sequence.
+template <int MODE, bool CTA2>
+struct TileLoop {
+  static constexpr bool AS = mode_astat(MODE, CTA2);
+  StatIter si;
+  int64_t t, npid;
+  __device__ __forceinline__ void init(const TcArgs& a, int64_t pid, int64_t npid_) {
+    t = pid; npid = npid_;
+    if (AS) si.init(a, (int)pid);
+  }
+  __device__ __forceinline__ bool next(const TcArgs& a, int rank, Work& w) {
+    if (AS) {
+      int m, n;
+      if (!si.next(m, n)) return false;
+      w.m0 = m * 2 * BM + rank * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK;
+      w.split = 0; w.n_tile = n; w.m_tile = m;
+      return true;
+    }
+    if (t >= a.total_tiles) return false;
+    w = get_work<MODE, CTA2>(a, t, rank);
+    t += npid;
+    return true;
+  }
+};
 
 // ---- epilogue helpers -----------------------------------------------------------------------------
 // Family variants of the B x C element transform (compile-time, so the hot loop carries no dead work):
@@ -448,9 +522,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr int BNT = mode_bn(MODE);                 // accumulator columns of one tile (256, DX: 512)
   constexpr int NBUF = mode_nbuf(MODE);
   constexpr bool IS_DW = (MODE == MODE_DW || MODE == MODE_DWF);
+  constexpr bool AS = mode_astat(MODE, CTA2);        // x^ tile resident in smem, only w^ streams
+  constexpr int A_IN_STAGE = AS ? 0 : A_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t tiles_base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;           // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t ares_base = smem_base;                             // AS: resident A, 8 k-blocks x 16 KB
+  const uint32_t tiles_base = smem_base + (AS ? A_RESIDENT_BYTES : 0);
   uint8_t* tiles_ptr = smem_raw + (tiles_base - raw_addr);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + STAGES * STAGE_BYTES);
   uint8_t* stg_all = tiles_ptr + STAGES * STAGE_BYTES + 256;        // output staging (BWD_G / DW / DWF only)
@@ -459,6 +537,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t bar_tfull = bar_empty + 8 * MAX_STAGES;            // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  const uint32_t bar_afull = bar_full + 8 * (2 * MAX_STAGES + 5);   // AS: resident A landed
+  const uint32_t bar_afree = bar_afull + 8;                         // AS: every MMA that read the resident A retired
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -473,6 +553,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS * NCTA);   // one arrive per epilogue warp (of both CTAs)
     }
+    mbar_init(bar_afull, NCTA);
+    mbar_init(bar_afree, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -490,12 +572,27 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // =============================== TMA producer (both CTAs of a pair) ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t t = pid; t < a.total_tiles; t += npid) {
-        const Work w = get_work<MODE, CTA2>(a, t, rank);
+      TileLoop<MODE, CTA2> tl;
+      tl.init(a, pid, npid);
+      Work w;
+      int res_m = -1;
+      uint32_t tile_j = 0;
+      while (tl.next(a, rank, w)) {
+        if (AS && w.m_tile != res_m) {
+          // (re)load the resident x^ tile: wait until every MMA of the previous tiles has retired
+          if (tile_j > 0) mbar_wait(bar_afree, (tile_j - 1) & 1);
+          if (rank == 0) mbar_expect_tx(bar_afull, NCTA * A_RESIDENT_BYTES); else mbar_arrive_cluster(bar_afull, 0);
+          for (int kb = 0; kb < MH_D / BK; ++kb) {
+            if (CTA2) tma_load_2d_2sm(ares_base + kb * A_STAGE_BYTES, &tmA, bar_afull, kb * BK, w.m0);
+            else tma_load_2d(ares_base + kb * A_STAGE_BYTES, &tmA, bar_afull, kb * BK, w.m0);
+          }
+          res_m = w.m_tile;
+        }
+        ++tile_j;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = tiles_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sb = sa + A_IN_STAGE;
           const uint32_t fb = bar_full + 8 * stage;
           if (!CTA2) {
             mbar_expect_tx(fb, STAGE_BYTES);
@@ -510,6 +607,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (MODE == MODE_DX) {
             // A = G, class-tiled [C_pad/128][B_pad][128]: k-block kb = classes 64kb.. -> slab kb/2, columns (kb&1)*64
             load(sa, &tmA, (kb & 1) * 64, (kb >> 1) * (int)a.B_pad + w.m0);  // box [64 k][128 rows]
+          } else if (AS) {
+            // x^ is resident
           } else if (!A_MN) {
             load(sa, &tmA, kb * BK, w.m0);                                  // box [64 k][128 rows]
           } else {
@@ -537,17 +636,26 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BM * NCTA, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
-      for (int64_t t = pid; t < a.total_tiles; t += npid, ++it) {
-        const Work w = get_work<MODE, CTA2>(a, t, rank);
+      TileLoop<MODE, CTA2> tl;
+      tl.init(a, pid, npid);
+      Work w;
+      int res_m = -1;
+      uint32_t aphase = 0;
+      for (; tl.next(a, rank, w); ++it) {
         const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
         mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);                       // epilogue(s) drained this accumulator
+        if (AS && w.m_tile != res_m) {
+          mbar_wait(bar_afull, aphase);
+          aphase ^= 1;
+          res_m = w.m_tile;
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = tiles_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sa = AS ? (ares_base + kb * A_STAGE_BYTES) : (tiles_base + stage * STAGE_BYTES);
+          const uint32_t sb = tiles_base + stage * STAGE_BYTES + A_IN_STAGE;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? desc_mnmajor(sa, k) : desc_kmajor(sa, k);
@@ -566,6 +674,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         // accumulator ready for the epilogue(s)
         if (CTA2) umma_commit_2sm(bar_tfull + 8 * buf); else umma_commit(bar_tfull + 8 * buf);
+        if (AS) { if (CTA2) umma_commit_2sm(bar_afree); else umma_commit(bar_afree); }
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -579,8 +688,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const float ha = (V == V_CURR) ? a.state[4] : p.hard_a;
     const float hb = p.hard_b, lo = p.lo, hi = p.hi;
     uint32_t it = 0;
-    for (int64_t t = pid; t < a.total_tiles; t += npid, ++it) {
-      const Work w = get_work<MODE, CTA2>(a, t, rank);
+    TileLoop<MODE, CTA2> tl;
+    tl.init(a, pid, npid);
+    Work w;
+    for (; tl.next(a, rank, w); ++it) {
       const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
       const int64_t row = (int64_t)w.m0 + r;
       RowCtx rc;
@@ -614,7 +725,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + cbase;
 
       FwdAcc acc{-INFINITY, 0.f, 0.f, 0};
-      uint8_t* stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;      // this warp's [32][272 B] staging rows
+      uint8_t* stg = stg_all + (warp - EPI_WARP0) * mode_stg_warp_bytes(MODE);   // this warp's staging rows
       uint32_t va[32], vb[32];
       tmem_ld32(taddr, va);
       tmem_ld_wait();
@@ -630,12 +741,27 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           uint32_t pk[16];
           float qv[32];
           bwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, pk, qv);
-          uint4* dst = reinterpret_cast<uint4*>(stg + lane * STG_ROW_BYTES + c * 64);
+          // stage 64 B of this row: 16 B piece index XOR (row & 7) -> conflict-free writes and reads
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((((c & 1) * 4 + k) ^ (lane & 7)) * 16)) =
+                make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
           if (a.rsum) {
             const float cs = warp_colsum32(qv, lane);                   // lane L: sum over this warp's 32 rows, column col0+L
             atomicAdd(a.rsum + w.n0 + col0 + lane, cs);
+          }
+          if (c & 1) {
+            // two chunks staged = [32 rows][64 classes = 128 B] -> global as full lines (8 lanes per row, 4 rows per
+            // instruction).  G is class-tiled [C_pad/128][B_pad][128]: this warp's 128 columns are one slab.
+            __syncwarp();
+            __nv_bfloat16* obase = a.G + (((int64_t)(w.n0 + cbase) / 128) * a.B_pad + w.m0 + q * 32) * 128 + (c - 1) * 32;
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+              const int rr = 4 * i2 + (lane >> 3);
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) * 16));
+              *reinterpret_cast<uint4*>(obase + (int64_t)rr * 128 + (lane & 7) * 8) = val;
+            }
+            __syncwarp();
           }
         } else if (MODE == MODE_DW || (MODE == MODE_DWF && a.layout == MH_LAYOUT_CD)) {
           float o[32];
@@ -706,19 +832,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) {
         if (CTA2) mbar_arrive_cluster(bar_tempty + 8 * buf, 0); else mbar_arrive(bar_tempty + 8 * buf);
-      }
-      if (MODE == MODE_BWD_G) {
-        // staged [32 rows][128 bf16 = 256 B] -> global, full lines: 16 lanes per row, 2 rows per instruction
-        // G is stored class-tiled: [C_pad/128][B_pad][128] (a 128-class slab of all rows is contiguous), so the dW
-        // GEMM reads one contiguous 256 KB block per class tile and this warp's 32 rows are 8 KB contiguous.
-        __nv_bfloat16* obase = a.G + (((int64_t)(w.n0 + cbase) / 128) * a.B_pad + w.m0 + q * 32) * 128;
-#pragma unroll
-        for (int i2 = 0; i2 < 16; ++i2) {
-          const int rr = 2 * i2 + (lane >> 4);
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * STG_ROW_BYTES + (lane & 15) * 16);
-          *reinterpret_cast<uint4*>(obase + (int64_t)rr * 128 + (lane & 15) * 8) = val;
-        }
-        __syncwarp();
       }
       if (MODE == MODE_FWD) {
         float* sp = a.stats_tiles + ((int64_t)w.n_tile * 2 + half) * MH_ST_PLANES * a.B_pad;
@@ -801,7 +914,8 @@ int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args
     attr_set = true;
   }
   const int units = CTA2 ? num_sms() / 2 : num_sms();
-  const int n = (int)std::min<int64_t>(args.total_tiles, units);
+  // A-stationary kernels use a static schedule over exactly `units` pairs (pairs without work exit at once)
+  const int n = mode_astat(MODE, CTA2) ? units : (int)std::min<int64_t>(args.total_tiles, units);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(CTA2 ? 2 * n : n);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -854,25 +968,76 @@ static int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
   return MH_OK;
 }
 
+// A-stationary schedule parameters for m_tiles <= units row tiles (see StatIter).
+static void make_sched(TcArgs& a, int units) {
+  a.sG = units / a.m_tiles;
+  a.sE = units - a.sG * a.m_tiles;
+  const int64_t wfix = (int64_t)a.sG * a.m_tiles;
+  a.n_fixed = a.sE == 0 ? a.n_tiles : (int)(((int64_t)a.n_tiles * wfix + (wfix + a.sE) / 2) / (wfix + a.sE));
+}
+
+// Test hook (host only, no device work): the (pair, m_tile, n_tile) triples of the A-stationary schedule in
+// execution order; returns the number of triples (<= cap are written) or a negative status.
+extern "C" int64_t mh_tc_schedule_tiles(int units, int m_tiles, int n_tiles, int32_t* out, int64_t cap) {
+  if (units <= 0 || m_tiles <= 0 || m_tiles > units || n_tiles <= 0) return MH_ERR_ARG;
+  TcArgs a{};
+  a.m_tiles = m_tiles; a.n_tiles = n_tiles;
+  make_sched(a, units);
+  int64_t cnt = 0;
+  for (int p = 0; p < units; ++p) {
+    StatIter it;
+    it.init(a, p);
+    int m, n;
+    while (it.next(m, n)) {
+      if (out && cnt < cap) { out[3 * cnt] = p; out[3 * cnt + 1] = m; out[3 * cnt + 2] = n; }
+      ++cnt;
+    }
+  }
+  return cnt;
+}
+
+// FWD / BWD_G launch.  cta2: A-stationary schedule; row tiles beyond `units` pairs go in further launches.
+template <int MODE>
+static int launch_s_tiles(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
+                          int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
+                          const float* state, const float* lse2, float* stats_tiles, void* G_bf16, float* r_colsum,
+                          cudaStream_t st) {
+  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
+  const int bmt = cta2 ? 2 * BM : BM;
+  const int units = cta2 ? num_sms() / 2 : num_sms();
+  CUtensorMap tb;
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, cta2 ? BN / 2 : BN)) return e;
+  const int64_t rows_per_launch = cta2 ? (int64_t)units * bmt : B_pad;
+  for (int64_t r0 = 0; r0 < B_pad; r0 += rows_per_launch) {
+    const int64_t rows = std::min(rows_per_launch, B_pad - r0);
+    if (r0 >= B) break;                                               // only padding rows left
+    CUtensorMap ta;
+    if (int e = make_tmap(&ta, (const __nv_bfloat16*)x_hat_bf16 + r0 * MH_D, rows, MH_D, BM)) return e;
+    TcArgs a{};
+    a.m_tiles = (int)(rows / bmt); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
+    a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
+    a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
+    if (cta2) make_sched(a, units);
+    a.p = mh_make_params(cfg_host);
+    a.B = B - r0; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
+    a.rowp = rowp + r0; a.ldp = ldp; a.label_local = label_local + r0; a.state = state;
+    a.lse2 = lse2 ? lse2 + r0 : nullptr;
+    a.stats_tiles = stats_tiles ? stats_tiles + r0 : nullptr;
+    a.G = G_bf16 ? (__nv_bfloat16*)G_bf16 + r0 * 128 : nullptr;
+    a.rsum = r_colsum;
+    if (int e = launch_variant<MODE>(ta, tb, a, cta2, st)) return e;
+  }
+  return MH_OK;
+}
+
 extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                              const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                              const int32_t* label_local, const float* state, float* stats_tiles, void* stream) {
   MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && stats_tiles, "null pointer");
   if (int e = check_common(B, B_pad, C, C_pad)) return e;
   MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
-  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
-  const int bmt = cta2 ? 2 * BM : BM;
-  CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, x_hat_bf16, B_pad, MH_D, BM)) return e;
-  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, cta2 ? BN / 2 : BN)) return e;
-  TcArgs a{};
-  a.m_tiles = (int)(B_pad / bmt); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
-  a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
-  a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
-  a.p = mh_make_params(cfg_host);
-  a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
-  a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.stats_tiles = stats_tiles;
-  return launch_variant<MODE_FWD>(ta, tb, a, cta2, (cudaStream_t)stream);
+  return launch_s_tiles<MODE_FWD>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+                                  nullptr, stats_tiles, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
@@ -882,22 +1047,9 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
   MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && lse2 && G_bf16, "null pointer");
   if (int e = check_common(B, B_pad, C, C_pad)) return e;
   MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
-  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
-  const int bmt = cta2 ? 2 * BM : BM;
-  CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, x_hat_bf16, B_pad, MH_D, BM)) return e;
-  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, cta2 ? BN / 2 : BN)) return e;
-  TcArgs a{};
-  a.m_tiles = (int)(B_pad / bmt); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
-  a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
-  a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
-  a.p = mh_make_params(cfg_host);
-  a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
-  a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state; a.lse2 = lse2;
-  a.G = (__nv_bfloat16*)G_bf16;
-  a.rsum = r_colsum;
   if (r_colsum) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
-  return launch_variant<MODE_BWD_G>(ta, tb, a, cta2, (cudaStream_t)stream);
+  return launch_s_tiles<MODE_BWD_G>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+                                    lse2, nullptr, G_bf16, r_colsum, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,

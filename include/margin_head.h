@@ -145,6 +145,11 @@ int mh_row_params(const mh_config* cfg_host, int64_t B, const float* xnorm, cons
 /* Number of statistics records the forward writes per row, = 2 * ceil(C_pad / MH_NTILE_FWD). */
 int64_t mh_fwd_num_tiles(int64_t C_pad);
 
+/* Host-only test hook: the static tile schedule of the A-stationary forward / backward-G kernels for `units` CTA
+ * pairs, m_tiles (<= units) 256-row tiles and n_tiles 256-class tiles.  Writes up to cap (pair, m_tile, n_tile)
+ * int32 triples in per-pair execution order and returns the total number of tiles scheduled (or a negative status). */
+int64_t mh_tc_schedule_tiles(int units, int m_tiles, int n_tiles, int32_t* out, int64_t cap);
+
 /* Fused cos-GEMM + margin + online softmax (replaces F.linear/torch.mm at criterion.py:65,176,267,
  * 408,545,868,990,1100,1256, the elementwise margin passes and nn.CrossEntropyLoss's log-softmax,
  * model_utils.py:179).  stats_tiles is [num_tiles, MH_ST_PLANES, B_pad]; nothing of size B x C is

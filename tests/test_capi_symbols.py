@@ -67,3 +67,29 @@ def test_no_cpu_fallback():
     y = torch.randint(0, 32, (4,))
     with pytest.raises(pkg._lib.MarginHeadError):
         head.fused_loss(x, y)
+
+
+@pytest.mark.parametrize("units,m_tiles,n_tiles", [(74, 4, 7813), (74, 1, 5), (74, 32, 977), (74, 74, 3), (74, 3, 42),
+                                                    (74, 2, 1), (74, 37, 400), (66, 5, 1000)])
+def test_a_stationary_schedule_covers_every_tile_once(lib, units, m_tiles, n_tiles):
+    """The static schedule of the A-stationary kernels (tc_head.cu StatIter): every (m, n) tile exactly once,
+    work balanced across pairs, and at most a handful of resident-tile reloads per pair."""
+    import numpy as np
+    total = m_tiles * n_tiles
+    out = np.full((total + 8, 3), -1, dtype=np.int32)
+    cnt = lib.mh_tc_schedule_tiles(units, m_tiles, n_tiles, out.ctypes.data_as(ctypes.c_void_p), total + 8)
+    assert cnt == total
+    out = out[:total]
+    seen = np.zeros((m_tiles, n_tiles), dtype=np.int64)
+    np.add.at(seen, (out[:, 1], out[:, 2]), 1)
+    assert (seen == 1).all()
+    per_pair = np.bincount(out[:, 0], minlength=units)
+    if total >= 20 * units:
+        assert per_pair.max() <= 1.03 * total / units + 2      # balanced to a few percent
+    for p in range(units):
+        ms = out[out[:, 0] == p, 1]
+        reloads = int((np.diff(ms) != 0).sum()) + (1 if len(ms) else 0)
+        assert reloads <= m_tiles + 1
+        if p < (units // m_tiles) * m_tiles:
+            assert reloads <= 1                                  # bound pairs never reload x^
+    assert lib.mh_tc_schedule_tiles(74, 75, 10, None, 0) < 0

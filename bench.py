@@ -187,6 +187,7 @@ def run_b200(args):
     else:
         head = pkg.ArcFace(D, Cn, s=64.0, m=0.5, easy_margin=False).to(dev)
         W = head.weight
+    eng = head.engine if world > 1 else head._engine
     g = torch.Generator(device=dev).manual_seed(4 + rank)
     with torch.no_grad():
         W.normal_(0, 0.01, generator=g)            # generated on the device per shard, never shipped through the host
@@ -272,6 +273,7 @@ def run_b200(args):
     algo = {
         "mh_tc_forward": ("tensor", gemm_flops), "mh_tc_backward_g": ("tensor", gemm_flops),
         "mh_tc_backward_dx": ("tensor", gemm_flops), "mh_tc_backward_dw": ("tensor", gemm_flops),
+        "mh_tc_backward_dw_fused": ("tensor", gemm_flops),
         "mh_prologue_w": ("hbm", 6.0 * C_loc * D + 4.0 * C_loc),
         "mh_norm_backward_w": ("hbm", (4.0 + 2.0 + 4.0) * C_loc * D),
     }
@@ -318,6 +320,8 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "B_per_gpu": B, "C": Cn, "d": D, "parallelism": f"class-shard x{world}",
+                       "backward": ("stash (forward writes bf16 exp2(z-ref); 3 GEMM passes per step)"
+                                    if eng.stash_ok() else "recompute (4 GEMM passes per step)"),
                        "l2": "inputs_exceed_l2 (W fp32 4.1 GB + bf16 2 GB per step vs 126 MB L2)", "loss": loss_val},
             "pct_of_bf16_peak": {"algorithmic_tflops": round(step_flops / (ms_total / args.steps * 1e-3) / 1e12 / world, 2),
                                  "of_burst": round(step_flops / world / (ms_total / args.steps * 1e-3) / 1e12 / peaks["tflops_burst"], 4),

@@ -52,9 +52,15 @@ SIGNATURES = {
     "mh_prologue_w": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp],
     "mh_prologue_x": [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_row_params": [_cfgp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
-    "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp],
+    "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
+    "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mh_tc_fixref_ok": [_cfgp, _i64],
+    "mh_tc_stash_ok": [_cfgp, _i64],
+    "mh_stash_prep": [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
+    "mh_stash_dx_combine": [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "mh_stash_dw_target": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
     "mh_tc_backward_dx": [_vp, _i64, _i64, _vp, _vp, C.POINTER(C.c_int), _vp],
     "mh_tc_backward_dw": [_vp, _i64, _i64, _vp, _vp, _vp],
     "mh_sgemm_strided": [_i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp],
@@ -115,6 +121,8 @@ def _launches(name: str, args) -> int:
         return 2 if int(args[1]) >= 256 else 1
     if name == "mh_tc_backward_dx":
         return 0 if not getattr(args[4], "value", None) else 1
+    if name == "mh_tc_backward_dx_stash":
+        return 0 if not getattr(args[7], "value", None) else 1
     return 1
 
 

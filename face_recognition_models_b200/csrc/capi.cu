@@ -67,3 +67,9 @@ MhParams mh_make_params(const mh_config* c) {
   }
   return p;
 }
+
+float mh_family_umax(const MhParams* p) {
+  if (p->hard_kind == 1) return fmaxf(1.f, p->hard_a + p->hard_b);   // MV: w*c + w - 1 at c = 1 (criterion.py:435)
+  if (p->hard_kind == 2) return 2.f;                                  // Curricular: c*(t+c), t <= 1 (criterion.py:575)
+  return 1.f;
+}

@@ -55,6 +55,8 @@ struct MhParams {
 };
 
 MhParams mh_make_params(const mh_config* c);
+// Upper bound of u = z / scale over non-target columns, per family (fixed-reference softmax, see mh_tc_fixref_ok).
+float mh_family_umax(const MhParams* p);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -1,72 +1,61 @@
-// Tensor-core path of the margin head for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed
-// 128B-swizzled shared-memory stages, mbarrier pipelines, warp-specialised persistent CTAs.
+// Tensor-core path of the margin head for sm_100a: tcgen05.mma (cta_group::2, one SM pair per tile) with TMEM
+// accumulators, TMA-fed 128B-swizzled shared-memory stages, mbarrier pipelines, warp-specialised persistent CTAs.
 //
-// One kernel skeleton, four modes (template parameter):
-//   FWD    S = x^ w^T tile  -> clamp/margin/scale -> online max/sum-exp + rank count per row.
-//          Nothing of size B x C is written (replaces criterion.py:267-301 & siblings +
-//          nn.CrossEntropyLoss, model_utils.py:179, + accuracy, metrics.py:3-16).
-//   BWD_G  recompute the S tile -> G = (P - Y) * dz/dcos as bf16, class-tiled [C_pad/128][B_pad][128].
-//          Also accumulates r_j = sum_i G_ij * cos_ij (= w^_j . dw^_j), the normalise-backward projection.
+// One kernel skeleton, five modes (template parameter):
+//   FWD    S = x^ w^T tile -> clamp/margin/scale -> sum-exp + rank count per row.  Nothing of size B x C is
+//          written (replaces criterion.py:267-301 & siblings + nn.CrossEntropyLoss, model_utils.py:179,
+//          + accuracy, metrics.py:3-16).
+//   FWDS   FWD that also stashes E' = exp2(z log2e - ref_i) * du/dcos as bf16 (target column and padding = 0), so a
+//          training step needs no logit recompute: G_ij = rho_i E'_ij with rho_i known once the row's lse is.
+//   BWD_G  recompute the S tile -> G = (P - Y) * dz/dcos as bf16 (the recompute backward).
+//          Both B x C layouts are class-tiled [C_pad/128][B_pad][128].
 //   DX     dx^ partials = G . w^      (A = G K-major,  B = w^ MN-major, split over classes; one 128 x 512
 //          accumulator = all 512 TMEM columns per CTA, so every G byte is read by exactly one CTA)
-//   DW     dw^          = G^T . x^    (A = G MN-major, B = x^ MN-major), raw fp32 output
-//   DWF    same GEMM, epilogue writes dW_j = g (dw^_j - w^_j r_j) / |w_j| straight into the parameter layout
+//          In stash mode the otherwise idle epilogue warps also read every A tile after its MMAs retired and
+//          accumulate r_j = sum_i G_ij cos_ij (= w^_j . dw^_j, the projection of the normalise-backward of W),
+//          recovering cos_ij from the stashed exponential itself.
+//   DW     dw^ = G^T . x^  (A = G MN-major, B = x^ MN-major), 256 classes x 256 d per pair tile; the epilogue writes
+//          dW_j = g (dw^_j - w^_j r_j) / |w_j| straight into the parameter layout (or raw dw^ on request).
 //
-// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11
-// epilogue (thread = one accumulator row x one 128-column half).  Tile 128 x 256 x 64, 4 smem stages
-// (48 KB each), two 256-column TMEM accumulators so the epilogue of tile t overlaps the MMAs of t+1.
+// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 TMEM allocator, warps 4-11
+// epilogue (thread = one accumulator row x one column half).
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdlib>
 #include <mutex>
-#include <map>
-#include <tuple>
+#include <algorithm>
 
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, MAX_STAGES = 6;
-constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
+constexpr int BMT = 2 * BM;                       // rows of a pair tile
+constexpr int A_STAGE_BYTES = BM * BK * 2;        // 16 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int STG_WARP_BYTES = 32 * 128;          // output staging per epilogue warp: 32 rows x 128 B, XOR-swizzled
+constexpr int DX_SIDE_BYTES = 2 * NUM_EPI_WARPS * 64 * 4 + 128 * 4;   // DX r_j side pass: partial sums (x2) + rho of the rows
 
-enum { MODE_FWD = 0, MODE_BWD_G = 1, MODE_DX = 2, MODE_DW = 3, MODE_DWF = 4 };
-// Per-mode pipeline configuration.  cta2 = the cta_group::2 variant: a cluster of two CTAs (one SM pair) computes a
-// 256-row tile; each CTA keeps its own 128 A rows + 128 accumulator lanes and loads only HALF of the B tile, the
-// tensor cores of both SMs read both halves.  Per-CTA bytes per MMA drop by a third to a half (the 1-CTA kernels
-// were bound by per-SM TMA/L2 request throughput), which also buys deeper pipelines.
-//
-// A-stationary (cta2 FWD / BWD_G): the pair's x^ tile (128 rows x 512 per CTA = 128 KB) stays resident in shared
+enum { MODE_FWD = 0, MODE_FWDS = 1, MODE_BWD_G = 2, MODE_DX = 3, MODE_DW = 4 };
+// A-stationary (FWD / FWDS / BWD_G): the pair's x^ tile (128 rows x 512 per CTA = 128 KB) stays resident in shared
 // memory while the pair sweeps class tiles, so only w^ streams (16 KB per CTA per k-block): L2 -> SM traffic per
 // tile halves (64 -> 32 B/clk/SM; the non-stationary kernels sat on the ~6.3 KB/clk chip-wide L2 delivery cap).
-constexpr bool mode_astat(int mode, bool cta2) { return cta2 && (mode == MODE_FWD || mode == MODE_BWD_G); }
+constexpr bool mode_astat(int mode) { return mode == MODE_FWD || mode == MODE_FWDS || mode == MODE_BWD_G; }
+constexpr bool mode_staged(int mode) { return mode == MODE_FWDS || mode == MODE_BWD_G || mode == MODE_DW; }
 constexpr int A_RESIDENT_BYTES = BM * MH_D * 2;                                   // 128 KB
-// Output staging for coalesced global stores, per epilogue warp:
-//   BWD_G: 32 rows x 128 B (64 bf16 columns), XOR-swizzled 16 B pieces, flushed every two 32-column chunks;
-//   DW/DWF: 32 rows x 256 B (+16 B pad per row), fp32 dw^ rows.
-constexpr int STG_ROW_BYTES = 256 + 16;
-constexpr int mode_stg_warp_bytes(int mode) {
-  return mode == MODE_BWD_G ? 32 * 128 : ((mode == MODE_DW || mode == MODE_DWF) ? 32 * STG_ROW_BYTES : 0);
-}
 constexpr int mode_bn(int mode) { return mode == MODE_DX ? 512 : 256; }          // accumulator columns per tile
-constexpr int mode_nbuf(int mode) { return mode == MODE_DX ? 1 : 2; }            // TMEM accumulators in flight
-constexpr int mode_stage_bytes(int mode, bool cta2) {
-  return (mode_astat(mode, cta2) ? 0 : A_STAGE_BYTES) + (mode_bn(mode) / (cta2 ? 2 : 1)) * BK * 2;
+constexpr int mode_nbuf(int mode) { return mode_bn(mode) == 512 ? 1 : 2; }        // TMEM accumulators in flight
+constexpr int mode_stage_bytes(int mode) { return (mode_astat(mode) ? 0 : A_STAGE_BYTES) + (mode_bn(mode) / 2) * BK * 2; }
+constexpr int mode_stages(int mode) { return (mode == MODE_FWD || mode == MODE_DW) ? 6 : 4; }
+constexpr int mode_smem_bytes(int mode) {
+  return (mode_astat(mode) ? A_RESIDENT_BYTES : 0) + mode_stages(mode) * mode_stage_bytes(mode) + 1024 /*align slack*/ +
+         256 /*barriers*/ + (mode_staged(mode) ? NUM_EPI_WARPS * STG_WARP_BYTES : 0) +
+         (mode == MODE_DX ? DX_SIDE_BYTES : 0);
 }
-constexpr int mode_stages(int mode, bool cta2) {
-  if (mode_astat(mode, cta2)) return mode == MODE_FWD ? 6 : 4;
-  if (cta2) return 4;
-  return mode == MODE_DX ? 2 : (mode_stg_warp_bytes(mode) ? 3 : 4);
-}
-constexpr int mode_smem_bytes(int mode, bool cta2) {
-  return (mode_astat(mode, cta2) ? A_RESIDENT_BYTES : 0) + mode_stages(mode, cta2) * mode_stage_bytes(mode, cta2) +
-         1024 /*align slack*/ + 256 /*barriers*/ + NUM_EPI_WARPS * mode_stg_warp_bytes(mode);
-}
-static_assert(mode_smem_bytes(MODE_BWD_G, false) <= 232448 && mode_smem_bytes(MODE_FWD, false) <= 232448 &&
-              mode_smem_bytes(MODE_DX, false) <= 232448 && mode_smem_bytes(MODE_BWD_G, true) <= 232448 &&
-              mode_smem_bytes(MODE_FWD, true) <= 232448 && mode_smem_bytes(MODE_DX, true) <= 232448 &&
-              mode_smem_bytes(MODE_DWF, true) <= 232448 && mode_smem_bytes(MODE_DWF, false) <= 232448, "smem budget");
+static_assert(mode_smem_bytes(MODE_FWD) <= 232448 && mode_smem_bytes(MODE_FWDS) <= 232448 &&
+              mode_smem_bytes(MODE_BWD_G) <= 232448 && mode_smem_bytes(MODE_DX) <= 232448 &&
+              mode_smem_bytes(MODE_DW) <= 232448, "smem budget");
 
 struct TcArgs {
   int m_tiles, n_tiles, n_split, k_blocks_total, k_blocks_per_split;
@@ -80,15 +69,20 @@ struct TcArgs {
   const float* state;
   const float* lse2;
   float* stats_tiles;
-  __nv_bfloat16* G;
+  __nv_bfloat16* G;            // BWD_G: G out; FWDS: stash out
   float* out;
   int64_t out_split_stride;
-  float* rsum;                 // BWD_G: r_j accumulation target [C_pad] (zeroed by the caller); DWF: read
-  const __nv_bfloat16* w_hat;  // DWF
-  const float* inv_norm;       // DWF
-  const float* gscal;          // DWF
-  int layout;                  // DWF: parameter layout of dW
-  int64_t ld;                  // DWF: row pitch of dW
+  int fixref;                  // FWD: fixed softmax reference (see mh_tc_fixref_ok); always 1 for FWDS
+  float umax;                  // upper bound of u = z / scale over non-target columns (fixref)
+  float* rsum;                 // r_j [C_pad]: DX (stash) accumulates into it, DW fused reads it
+  const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
+  float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
+  const __nv_bfloat16* w_hat;  // DW fused
+  const float* inv_norm;       // DW fused
+  const float* gscal;          // DW fused
+  int raw_dw;                  // DW: write raw dw^ [C_pad, 512] instead of the projected dW
+  int layout;                  // DW fused: parameter layout of dW
+  int64_t ld;                  // DW fused: row pitch of dW
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -100,7 +94,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -123,41 +117,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// L2 prefetch of a TMA box (no shared memory, no barrier): hides HBM latency beyond the smem pipeline depth.
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -264,32 +228,7 @@ struct Work {
   int m_tile;        // A-stationary modes: row-tile index (the resident x^ tile)
 };
 
-// Tile -> work.  BMT = rows of the (pair) tile: 128, or 256 with cta_group::2; `rank` selects this CTA's 128 rows.
-template <int MODE, bool CTA2>
-__device__ __forceinline__ Work get_work(const TcArgs& a, int64_t t, int rank) {
-  constexpr int BMT = CTA2 ? 2 * BM : BM;
-  Work w;
-  w.split = 0;
-  w.n_tile = 0;
-  w.m_tile = 0;
-  if (MODE == MODE_FWD || MODE == MODE_BWD_G) {
-    int m = (int)(t % a.m_tiles), n = (int)(t / a.m_tiles);
-    w.m0 = m * BMT + rank * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK; w.n_tile = n;
-  } else if (MODE == MODE_DX) {
-    w.split = (int)(t / a.m_tiles);
-    w.m0 = (int)(t % a.m_tiles) * BMT + rank * BM;
-    w.n0 = 0;
-    w.kb0 = w.split * a.k_blocks_per_split;
-    w.kb1 = min(a.k_blocks_total, w.kb0 + a.k_blocks_per_split);
-  } else {
-    w.m0 = (int)(t >> 1) * BMT + rank * BM;
-    w.n0 = (int)(t & 1) * BN;
-    w.kb0 = 0; w.kb1 = a.k_blocks_total;
-  }
-  return w;
-}
-
-// A-stationary tile schedule (cta2 FWD / BWD_G).  `units` CTA pairs, m_tiles <= units row tiles of 256 rows:
+// A-stationary tile schedule (FWD / FWDS / BWD_G).  `units` CTA pairs, m_tiles <= units row tiles of 256 rows:
 //   * sG = units / m_tiles pairs are bound to each row tile m; pair q of the group takes class tiles q, q+sG, ... of
 //     [0, n_fixed).  The groups of all row tiles sweep the classes in lockstep, so a w^ tile fetched from HBM by one
 //     row tile is an L2 hit for the others.
@@ -324,26 +263,36 @@ struct StatIter {
   }
 };
 
-// The tile sequence of one CTA (pair); the producer, MMA and epilogue roles all walk the same sequence.
-template <int MODE, bool CTA2>
+// The tile sequence of one CTA pair; the producer, MMA and epilogue roles all walk the same sequence.
+template <int MODE>
 struct TileLoop {
-  static constexpr bool AS = mode_astat(MODE, CTA2);
   StatIter si;
   int64_t t, npid;
   __device__ __forceinline__ void init(const TcArgs& a, int64_t pid, int64_t npid_) {
     t = pid; npid = npid_;
-    if (AS) si.init(a, (int)pid);
+    if (mode_astat(MODE)) si.init(a, (int)pid);
   }
   __device__ __forceinline__ bool next(const TcArgs& a, int rank, Work& w) {
-    if (AS) {
+    w.split = 0; w.n_tile = 0; w.m_tile = 0;
+    if (mode_astat(MODE)) {
       int m, n;
       if (!si.next(m, n)) return false;
-      w.m0 = m * 2 * BM + rank * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK;
-      w.split = 0; w.n_tile = n; w.m_tile = m;
+      w.m0 = m * BMT + rank * BM; w.n0 = n * BN; w.kb0 = 0; w.kb1 = MH_D / BK;
+      w.n_tile = n; w.m_tile = m;
       return true;
     }
     if (t >= a.total_tiles) return false;
-    w = get_work<MODE, CTA2>(a, t, rank);
+    if (MODE == MODE_DX) {
+      w.split = (int)(t / a.m_tiles);
+      w.m0 = (int)(t % a.m_tiles) * BMT + rank * BM;
+      w.n0 = 0;
+      w.kb0 = w.split * a.k_blocks_per_split;
+      w.kb1 = min(a.k_blocks_total, w.kb0 + a.k_blocks_per_split);
+    } else {  // DW: 256 classes x one 256-wide half of d
+      w.m0 = (int)(t >> 1) * BMT + rank * BM;
+      w.n0 = (int)(t & 1) * BN;
+      w.kb0 = 0; w.kb1 = a.k_blocks_total;
+    }
     t += npid;
     return true;
   }
@@ -360,14 +309,19 @@ enum { V_PLAIN = 0, V_CLAMP = 1, V_SPHERE = 2, V_MV = 3, V_CURR = 4, V_NONE = 5 
 
 struct RowCtx {
   float scale, scale2, thr, t, zt2, dzt, lse2;
+  float nref2;       // fixref: -(softmax reference) in log2 units = 102 - scale2 * umax
+  float ntbig;       // fixref: -t * 2^60 (rank count through FFMA.SAT)
   int tcol;          // tile-local target column, or -1
   bool valid;        // row < B
 };
 
 struct FwdAcc {
   float m, l, ez;
+  float cntf;
   int cnt;
 };
+
+constexpr float CNT_BIG = 1152921504606846976.f;   // 2^60
 
 template <int V>
 __device__ __forceinline__ float elem_u(float raw, float lo, float hi, float thr, float ha, float hb, float& c_out) {
@@ -387,7 +341,12 @@ __device__ __forceinline__ float elem_du(float raw, float c, float thr, float ha
   return du;
 }
 
-// One 32-column chunk of the forward: online max / sum-exp (log2 domain), rank count, optional sum e*u.
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One 32-column chunk of the forward, general form: online max / sum-exp (log2 domain), rank count, optional sum e*u.
 template <int V>
 __device__ __forceinline__ void fwd_chunk(uint32_t (&v)[32], int col0, int nvalid, const RowCtx& rc, float lo,
                                           float hi, float ha, float hb, FwdAcc& acc) {
@@ -447,6 +406,57 @@ __device__ __forceinline__ void fwd_chunk(uint32_t (&v)[32], int col0, int nvali
   }
 }
 
+// One 32-column chunk of the forward with a FIXED softmax reference (no running max, no rescale):
+// e = exp2(u*scale2 - ref2_i) with ref2_i = scale2_i*umax - 102, valid when every possible non-target term is a normal
+// fp32/bf16 number (mh_tc_fixref_ok).  5 issue slots per element: FFMA, MUFU.EX2, FADD (sum), FFMA.SAT, FADD (rank
+// count: sat((c - t) * 2^60) is exactly 1 for c > t, else 0).  STASH: E' = e * du/dcos -> 16 packed bf16 pairs.
+template <int V, bool STASH>
+__device__ __forceinline__ void fwd_chunk_fix(const uint32_t (&v)[32], int col0, int nvalid, const RowCtx& rc, float lo,
+                                              float hi, float ha, float hb, FwdAcc& acc, uint32_t (&pk)[16]) {
+  const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid) || (STASH && !rc.valid);
+  if (!slow) {
+    float l2[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      float es[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float raw = __uint_as_float(v[k + h]);
+        float c;
+        const float u = elem_u<V>(raw, lo, hi, rc.thr, ha, hb, c);
+        c2[h] += __saturatef(fmaf(c, CNT_BIG, rc.ntbig));
+        const float e = ex2(fmaf(u, rc.scale2, rc.nref2));
+        l2[h] += e;
+        es[h] = STASH ? e * elem_du<V>(raw, c, rc.thr, ha) : e;
+      }
+      if (STASH) pk[k >> 1] = pack_bf16(es[0], es[1]);
+    }
+    acc.l += l2[0] + l2[1];
+    acc.cntf += c2[0] + c2[1];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      float es[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float raw = __uint_as_float(v[k + h]);
+        float c;
+        const float u = elem_u<V>(raw, lo, hi, rc.thr, ha, hb, c);
+        const int col = col0 + k + h;
+        float e = ex2(fmaf(u, rc.scale2, rc.nref2));
+        float sv = e * elem_du<V>(raw, c, rc.thr, ha);
+        if (col == rc.tcol) { e = ex2(rc.zt2 + rc.nref2); sv = 0.f; }
+        else if (col < nvalid && c > rc.t) acc.cnt += 1;
+        if (col >= nvalid) { e = 0.f; sv = 0.f; }
+        if (!rc.valid) sv = 0.f;
+        acc.l += e;
+        es[h] = sv;
+      }
+      if (STASH) pk[k >> 1] = pack_bf16(es[0], es[1]);
+    }
+  }
+}
+
 // Column sums over the 32 lanes of a warp of a 32-register array: on return lane L holds sum_lanes x[L].
 // Transposed butterfly: 31 shuffles, no shared memory.
 __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
@@ -483,8 +493,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int
         g2[h] = pr * rc.scale * elem_du<V>(raw, c, rc.thr, ha);
         qv[k + h] = g2[h] * raw;
       }
-      __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
-      pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
+      pk[k >> 1] = pack_bf16(g2[0], g2[1]);
     }
   } else {
 #pragma unroll
@@ -503,27 +512,66 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&v)[32], int col0, int
         g2[h] = g;
         qv[k + h] = g * raw;
       }
-      __nv_bfloat162 b = __floats2bfloat162_rn(g2[0], g2[1]);
-      pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b);
+      pk[k >> 1] = pack_bf16(g2[0], g2[1]);
     }
   }
 }
 
-template <int MODE, int V, bool CTA2>
+// Stage one 64 B half-row (16 packed bf16 pairs) of a [32 rows][128 B] warp staging tile; 16 B pieces XOR-swizzled
+// with the row so that both the row-wise writes and the 4-rows-per-instruction reads are bank-conflict free.
+__device__ __forceinline__ void stage_half_row(uint8_t* stg, int lane, int half64, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<uint4*>(stg + lane * 128 + (((half64 * 4 + k) ^ (lane & 7)) * 16)) =
+        make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+}
+// Flush a staged [32 rows][128 B] tile: 8 lanes per row (full 128 B lines), 4 rows per instruction.
+// dst = address of row 0 / byte 0 of the tile in global memory, pitch in bytes; rows >= rows_ok are skipped.
+__device__ __forceinline__ void flush_tile(const uint8_t* stg, int lane, uint8_t* dst, int64_t pitch_bytes, int rows_ok) {
+#pragma unroll
+  for (int i2 = 0; i2 < 8; ++i2) {
+    const int rr = 4 * i2 + (lane >> 3);
+    const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) * 16));
+    if (rr < rows_ok) *reinterpret_cast<uint4*>(dst + (int64_t)rr * pitch_bytes + (lane & 7) * 16) = val;
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Walk the NCHUNK 32-column chunks of this thread's accumulator row: the TMEM load of chunk c+1 is in flight while
+// chunk c is processed.  loaded() runs once every TMEM read of the row has completed (before the last chunk's body).
+template <int NCHUNK, class Body, class Loaded>
+__device__ __forceinline__ void chunk_loop(uint32_t taddr, Body&& body, Loaded&& loaded) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr, va);
+  tmem_ld_wait();
+  if (NCHUNK == 1) loaded();
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? vb : va;
+    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+    if (c + 1 < NCHUNK) tmem_ld32(taddr + (c + 1) * 32, nxt);
+    body(c, cur);
+    if (c + 1 < NCHUNK) tmem_ld_wait();
+    if (c + 2 == NCHUNK) loaded();
+  }
+}
+
+template <int MODE, int V>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  constexpr int STAGES = mode_stages(MODE, CTA2);
-  constexpr int STAGE_BYTES = mode_stage_bytes(MODE, CTA2);
-  constexpr int NCTA = CTA2 ? 2 : 1;
-  constexpr int GW = BN / NCTA;                      // B columns (of one 256-wide UMMA group) held by this CTA
-  const int rank = CTA2 ? (int)cluster_ctarank() : 0;
-  const int64_t pid = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;        // tile-scheduling unit: CTA or CTA pair
-  const int64_t npid = CTA2 ? (gridDim.x >> 1) : gridDim.x;
-  constexpr int BNT = mode_bn(MODE);                 // accumulator columns of one tile (256, DX: 512)
-  constexpr int NBUF = mode_nbuf(MODE);
-  constexpr bool IS_DW = (MODE == MODE_DW || MODE == MODE_DWF);
-  constexpr bool AS = mode_astat(MODE, CTA2);        // x^ tile resident in smem, only w^ streams
+  constexpr int STAGES = mode_stages(MODE);
+  constexpr int STAGE_BYTES = mode_stage_bytes(MODE);
+  constexpr bool AS = mode_astat(MODE);              // x^ tile resident in smem, only w^ streams
   constexpr int A_IN_STAGE = AS ? 0 : A_STAGE_BYTES;
+  constexpr int GW = BN / 2;                         // B columns (of one 256-wide UMMA group) held by this CTA
+  constexpr int BNT = mode_bn(MODE);                 // accumulator columns of one tile (256; DX, DW: 512)
+  constexpr int NBUF = mode_nbuf(MODE);
+  constexpr bool A_MN = (MODE == MODE_DW);
+  constexpr bool B_MN = (MODE == MODE_DX || MODE == MODE_DW);
+  const int rank = (int)cluster_ctarank();
+  const int64_t pid = blockIdx.x >> 1;               // tile-scheduling unit: CTA pair
+  const int64_t npid = gridDim.x >> 1;
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;           // SWIZZLE_128B needs 1024 B alignment
@@ -531,7 +579,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t tiles_base = smem_base + (AS ? A_RESIDENT_BYTES : 0);
   uint8_t* tiles_ptr = smem_raw + (tiles_base - raw_addr);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + STAGES * STAGE_BYTES);
-  uint8_t* stg_all = tiles_ptr + STAGES * STAGE_BYTES + 256;        // output staging (BWD_G / DW / DWF only)
+  uint8_t* stg_all = tiles_ptr + STAGES * STAGE_BYTES + 256;        // output staging (FWDS / BWD_G / DW)
   const uint32_t bar_full = smem_u32(bars);                         // [STAGES]
   const uint32_t bar_empty = bar_full + 8 * MAX_STAGES;             // [STAGES]
   const uint32_t bar_tfull = bar_empty + 8 * MAX_STAGES;            // [2]
@@ -539,6 +587,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   const uint32_t bar_afull = bar_full + 8 * (2 * MAX_STAGES + 5);   // AS: resident A landed
   const uint32_t bar_afree = bar_afull + 8;                         // AS: every MMA that read the resident A retired
+  const uint32_t bar_rdone = bar_afree + 8;                         // DX side pass: [STAGES] the epilogue warps read the A tile
+  float* side_red = reinterpret_cast<float*>(stg_all);              // DX side pass: [2][8 warps][64]
+  float* side_rho = side_red + 2 * NUM_EPI_WARPS * 64;              // DX side pass: [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -546,33 +597,29 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, NCTA);                // pair: leader's expect_tx arrive + the peer producer's arrive
+      mbar_init(bar_full + 8 * s, 2);                   // leader's expect_tx arrive + the peer producer's arrive
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS * NCTA);   // one arrive per epilogue warp (of both CTAs)
+      mbar_init(bar_tempty + 8 * b, NUM_EPI_WARPS * 2);   // one arrive per epilogue warp of both CTAs
     }
-    mbar_init(bar_afull, NCTA);
+    mbar_init(bar_afull, 2);
     mbar_init(bar_afree, 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(bar_rdone + 8 * s, NUM_EPI_WARPS);
     fence_barrier_init();
   }
-  if (warp == 2) {
-    if (CTA2) tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS); else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-  }
+  if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
-  if (CTA2) cluster_sync_all(); else __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  constexpr bool A_MN = IS_DW;
-  constexpr bool B_MN = (MODE == MODE_DX || IS_DW);
-
   if (warp == 0) {
-    // =============================== TMA producer (both CTAs of a pair) ===============================
+    // =============================== TMA producer (both CTAs of the pair) ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      TileLoop<MODE, CTA2> tl;
+      TileLoop<MODE> tl;
       tl.init(a, pid, npid);
       Work w;
       int res_m = -1;
@@ -581,50 +628,37 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (AS && w.m_tile != res_m) {
           // (re)load the resident x^ tile: wait until every MMA of the previous tiles has retired
           if (tile_j > 0) mbar_wait(bar_afree, (tile_j - 1) & 1);
-          if (rank == 0) mbar_expect_tx(bar_afull, NCTA * A_RESIDENT_BYTES); else mbar_arrive_cluster(bar_afull, 0);
-          for (int kb = 0; kb < MH_D / BK; ++kb) {
-            if (CTA2) tma_load_2d_2sm(ares_base + kb * A_STAGE_BYTES, &tmA, bar_afull, kb * BK, w.m0);
-            else tma_load_2d(ares_base + kb * A_STAGE_BYTES, &tmA, bar_afull, kb * BK, w.m0);
-          }
+          if (rank == 0) mbar_expect_tx(bar_afull, 2 * A_RESIDENT_BYTES); else mbar_arrive_cluster(bar_afull, 0);
+          for (int kb = 0; kb < MH_D / BK; ++kb)
+            tma_load_2d_2sm(ares_base + kb * A_STAGE_BYTES, &tmA, bar_afull, kb * BK, w.m0);
           res_m = w.m_tile;
         }
         ++tile_j;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (MODE == MODE_DX && a.rho) mbar_wait(bar_rdone + 8 * stage, phase ^ 1);   // side pass has read the A tile
           const uint32_t sa = tiles_base + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_IN_STAGE;
           const uint32_t fb = bar_full + 8 * stage;
-          if (!CTA2) {
-            mbar_expect_tx(fb, STAGE_BYTES);
-          } else if (rank == 0) {
-            mbar_expect_tx(fb, 2 * STAGE_BYTES);                            // bytes of both CTAs land on the leader's barrier
-          } else {
-            mbar_arrive_cluster(fb, 0);
-          }
-          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
-            if (CTA2) tma_load_2d_2sm(dst, m, fb, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
-          };
+          // the bytes of both CTAs land on the leader's barrier
+          if (rank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES); else mbar_arrive_cluster(fb, 0);
           if (MODE == MODE_DX) {
             // A = G, class-tiled [C_pad/128][B_pad][128]: k-block kb = classes 64kb.. -> slab kb/2, columns (kb&1)*64
-            load(sa, &tmA, (kb & 1) * 64, (kb >> 1) * (int)a.B_pad + w.m0);  // box [64 k][128 rows]
-          } else if (AS) {
-            // x^ is resident
-          } else if (!A_MN) {
-            load(sa, &tmA, kb * BK, w.m0);                                  // box [64 k][128 rows]
-          } else {
-            // A = G^T from the class-tiled G: this CTA's 128 classes are slab m0/128; box [64 classes][64 rows]
+            tma_load_2d_2sm(sa, &tmA, fb, (kb & 1) * 64, (kb >> 1) * (int)a.B_pad + w.m0);   // box [64 k][128 rows]
+          } else if (MODE == MODE_DW) {
+            // A = G^T from the class-tiled G: this CTA's 128 classes are slab m0/128; boxes [64 classes][64 rows]
 #pragma unroll
             for (int bx = 0; bx < BM / 64; ++bx)
-              load(sa + bx * 8192, &tmA, 64 * bx, (w.m0 / 128) * (int)a.B_pad + kb * BK);
+              tma_load_2d_2sm(sa + bx * 8192, &tmA, fb, 64 * bx, (w.m0 / 128) * (int)a.B_pad + kb * BK);
           }
           if (!B_MN) {
-            load(sb, &tmB, kb * BK, w.n0 + rank * GW);                      // box [64 k][GW rows]
+            tma_load_2d_2sm(sb, &tmB, fb, kb * BK, w.n0 + rank * GW);                        // box [64 k][128 rows]
           } else {
 #pragma unroll
             for (int nh = 0; nh < BNT / BN; ++nh)
 #pragma unroll
               for (int bx = 0; bx < GW / 64; ++bx)
-                load(sb + (nh * (GW / 64) + bx) * 8192, &tmB, w.n0 + nh * BN + rank * GW + 64 * bx, kb * BK);
+                tma_load_2d_2sm(sb + (nh * (GW / 64) + bx) * 8192, &tmB, fb, w.n0 + nh * BN + rank * GW + 64 * bx, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -633,17 +667,17 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BM * NCTA, BN);
+      constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BMT, BN);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
-      TileLoop<MODE, CTA2> tl;
+      TileLoop<MODE> tl;
       tl.init(a, pid, npid);
       Work w;
       int res_m = -1;
       uint32_t aphase = 0;
       for (; tl.next(a, rank, w); ++it) {
         const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
-        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);                       // epilogue(s) drained this accumulator
+        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);                       // epilogues drained this accumulator
         if (AS && w.m_tile != res_m) {
           mbar_wait(bar_afull, aphase);
           aphase ^= 1;
@@ -661,20 +695,17 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint64_t da = A_MN ? desc_mnmajor(sa, k) : desc_kmajor(sa, k);
             const uint32_t acc = (kb > w.kb0 || k > 0) ? 1u : 0u;
 #pragma unroll
-            for (int nh = 0; nh < BNT / BN; ++nh) {                       // DX: two N=256 groups of the 512-wide tile
+            for (int nh = 0; nh < BNT / BN; ++nh) {                       // DX, DW: two N=256 groups of the 512-wide tile
               const uint32_t sbh = sb + nh * (GW / 64) * 8192;
               const uint64_t db = B_MN ? desc_mnmajor(sbh, k) : desc_kmajor(sbh, k);
-              if (CTA2) umma_bf16_2sm(tmem_d + nh * BN, da, db, idesc, acc);
-              else umma_bf16(tmem_d + nh * BN, da, db, idesc, acc);
+              umma_bf16_2sm(tmem_d + nh * BN, da, db, idesc, acc);
             }
           }
-          // frees the smem stage (in both CTAs) when the MMAs retire
-          if (CTA2) umma_commit_2sm(bar_empty + 8 * stage); else umma_commit(bar_empty + 8 * stage);
+          umma_commit_2sm(bar_empty + 8 * stage);      // frees the smem stage in both CTAs when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator ready for the epilogue(s)
-        if (CTA2) umma_commit_2sm(bar_tfull + 8 * buf); else umma_commit(bar_tfull + 8 * buf);
-        if (AS) { if (CTA2) umma_commit_2sm(bar_afree); else umma_commit(bar_afree); }
+        umma_commit_2sm(bar_tfull + 8 * buf);          // accumulator ready for the epilogues
+        if (AS) umma_commit_2sm(bar_afree);
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -683,171 +714,189 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int q = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;
     const int r = q * 32 + lane;                    // row of the tile owned by this thread
-    constexpr int NCHUNK = (BNT / 2) / 32;          // 32-column chunks per warp (4, DX: 8)
+    constexpr int NCHUNK = (BNT / 2) / 32;          // 32-column chunks per warp (4; DX, DW: 8)
     const MhParams& p = a.p;
     const float ha = (V == V_CURR) ? a.state[4] : p.hard_a;
     const float hb = p.hard_b, lo = p.lo, hi = p.hi;
+    uint8_t* stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;      // this warp's staging tile
     uint32_t it = 0;
-    TileLoop<MODE, CTA2> tl;
+    uint32_t side_stage = 0, side_phase = 0;          // DX side pass: walks the smem stages like the producer
+    TileLoop<MODE> tl;
     tl.init(a, pid, npid);
     Work w;
     for (; tl.next(a, rank, w); ++it) {
       const uint32_t buf = it % NBUF, bphase = (it / NBUF) & 1;
       const int64_t row = (int64_t)w.m0 + r;
-      RowCtx rc;
-      rc.valid = true; rc.tcol = -1;
-      if (MODE == MODE_FWD || MODE == MODE_BWD_G) {
+      const int cbase = half * (BNT / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + cbase;
+      auto release = [&]() {
+        // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * buf, 0);
+      };
+      auto no_op = [&]() {};
+
+      if (AS) {
+        RowCtx rc;
         rc.valid = row < a.B;
+        rc.tcol = -1;
         rc.scale = a.rowp[MH_RP_SCALE * a.ldp + row];
         rc.scale2 = rc.scale * MH_LOG2E;
         rc.thr = a.rowp[MH_RP_THR * a.ldp + row];
         rc.t = a.rowp[MH_RP_T * a.ldp + row];
         rc.zt2 = a.rowp[MH_RP_ZT * a.ldp + row] * MH_LOG2E;
         rc.dzt = a.rowp[MH_RP_DZT * a.ldp + row];
+        rc.nref2 = 102.f - rc.scale2 * a.umax;
+        rc.ntbig = -rc.t * CNT_BIG;
         const int32_t y = a.label_local[row];
         if (y >= w.n0 && y < w.n0 + BN) rc.tcol = y - w.n0;
         rc.lse2 = (MODE == MODE_BWD_G && rc.valid) ? a.lse2[row] : 0.f;
-      }
-      // DWF: this thread owns class `row`; dW_j = coef * (dw^_j - w^_j * rj)
-      float dwf_rj = 0.f, dwf_coef = 0.f;
-      bool dwf_ok = false;
-      if (MODE == MODE_DWF) {
-        dwf_ok = row < a.C;
-        if (dwf_ok) {
-          dwf_rj = a.rsum[row];
-          dwf_coef = a.gscal[0] * a.inv_norm[row];
-        }
-      }
-      const int nvalid = (int)min((int64_t)BN, a.C - (int64_t)w.n0);   // valid class columns in this tile (FWD/BWD_G)
-      const int cbase = half * (BNT / 2);
-      mbar_wait(bar_tfull + 8 * buf, bphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + cbase;
-
-      FwdAcc acc{-INFINITY, 0.f, 0.f, 0};
-      uint8_t* stg = stg_all + (warp - EPI_WARP0) * mode_stg_warp_bytes(MODE);   // this warp's staging rows
-      uint32_t va[32], vb[32];
-      tmem_ld32(taddr, va);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        uint32_t (&cur)[32] = (c & 1) ? vb : va;
-        uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-        if (c + 1 < NCHUNK) tmem_ld32(taddr + (c + 1) * 32, nxt);   // prefetch while this chunk is processed
-        const int col0 = cbase + c * 32;
-        if (MODE == MODE_FWD) {
-          fwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc);
-        } else if (MODE == MODE_BWD_G) {
+        const int nvalid = (int)min((int64_t)BN, a.C - (int64_t)w.n0);   // valid class columns in this tile
+        const bool fix = (MODE == MODE_FWDS) || (MODE == MODE_FWD && V != V_SPHERE && a.fixref);
+        FwdAcc acc{-INFINITY, 0.f, 0.f, 0.f, 0};
+        mbar_wait(bar_tfull + 8 * buf, bphase);
+        tc_fence_after();
+        chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
+          const int col0 = cbase + c * 32;
           uint32_t pk[16];
-          float qv[32];
-          bwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, pk, qv);
-          // stage 64 B of this row: 16 B piece index XOR (row & 7) -> conflict-free writes and reads
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((((c & 1) * 4 + k) ^ (lane & 7)) * 16)) =
-                make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-          if (a.rsum) {
-            const float cs = warp_colsum32(qv, lane);                   // lane L: sum over this warp's 32 rows, column col0+L
-            atomicAdd(a.rsum + w.n0 + col0 + lane, cs);
+          if (MODE == MODE_FWD) {
+            if (V != V_SPHERE && fix) fwd_chunk_fix<V == V_SPHERE ? V_CLAMP : V, false>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc, pk);
+            else fwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc);
+          } else {
+            if (MODE == MODE_FWDS) {
+              fwd_chunk_fix<V == V_SPHERE ? V_CLAMP : V, true>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc, pk);
+            } else {
+              float qv[32];
+              bwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, pk, qv);
+              if (a.rsum) {
+                const float cs = warp_colsum32(qv, lane);           // lane L: sum over this warp's 32 rows, column col0+L
+                atomicAdd(a.rsum + w.n0 + col0 + lane, cs);
+              }
+            }
+            stage_half_row(stg, lane, c & 1, pk);
+            if (c & 1) {
+              // two chunks staged = [32 rows][64 classes = 128 B] -> global as full lines.  The B x C buffer is
+              // class-tiled [C_pad/128][B_pad][128]: this warp's 128 columns are one slab.
+              __syncwarp();
+              __nv_bfloat16* obase = a.G + (((int64_t)(w.n0 + cbase) / 128) * a.B_pad + w.m0 + q * 32) * 128 + (c - 1) * 32;
+              flush_tile(stg, lane, reinterpret_cast<uint8_t*>(obase), 256, 32);
+              __syncwarp();
+            }
           }
-          if (c & 1) {
-            // two chunks staged = [32 rows][64 classes = 128 B] -> global as full lines (8 lanes per row, 4 rows per
-            // instruction).  G is class-tiled [C_pad/128][B_pad][128]: this warp's 128 columns are one slab.
-            __syncwarp();
-            __nv_bfloat16* obase = a.G + (((int64_t)(w.n0 + cbase) / 128) * a.B_pad + w.m0 + q * 32) * 128 + (c - 1) * 32;
+        }, release);
+        if (MODE == MODE_FWD || MODE == MODE_FWDS) {
+          float* sp = a.stats_tiles + ((int64_t)w.n_tile * 2 + half) * MH_ST_PLANES * a.B_pad;
+          sp[MH_ST_M * a.B_pad + row] = fix ? -rc.nref2 : acc.m;
+          sp[MH_ST_L * a.B_pad + row] = acc.l;
+          sp[MH_ST_CNT * a.B_pad + row] = (float)acc.cnt + acc.cntf;
+          sp[MH_ST_EZ * a.B_pad + row] = (V == V_SPHERE) ? acc.ez : 0.f;
+        }
+      } else if (MODE == MODE_DX) {
+        if (a.rho) {
+          // ---- side pass (stash mode): r_j += sum_i rho_i E'_ij cos_ij over this CTA's 128 rows, k-block by k-block.
+          // An A tile is [128 rows][64 classes] (128 B rows, 16 B chunks XOR-swizzled with row & 7); it is read once its
+          // MMAs have retired (bar_empty) and handed back to the producer through bar_rdone.  cos_ij is recovered from
+          // the stash: E' = exp2(s2 cos - ref2)  =>  cos = log2(E') / s2 + ref2 / s2  (E' = 0: target / clamped / pad).
+          const int ew = warp - EPI_WARP0;
+          if (threadIdx.x - EPI_WARP0 * 32 < 128) side_rho[threadIdx.x - EPI_WARP0 * 32] = a.rho[w.m0 + (threadIdx.x - EPI_WARP0 * 32)];
+          epi_bar_sync();
+          for (int kb = w.kb0; kb < w.kb1; ++kb) {
+            mbar_wait(bar_empty + 8 * side_stage, side_phase);
+            const uint32_t sa = tiles_base + side_stage * STAGE_BYTES;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
-              const int rr = 4 * i2 + (lane >> 3);
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) * 16));
-              *reinterpret_cast<uint4*>(obase + (int64_t)rr * 128 + (lane & 7) * 8) = val;
+            for (int rr = 0; rr < 16; ++rr) {
+              const int ar = ew * 16 + rr;
+              uint32_t word;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word)
+                           : "r"(sa + ar * 128 + ((((lane >> 2) ^ (ar & 7)) << 4) | ((lane & 3) << 2))));
+              const float v0 = __uint_as_float(word << 16), v1 = __uint_as_float(word & 0xffff0000u);
+              const float rh = side_rho[ar];
+              const float c0 = fmaf(fmaxf(__log2f(v0), -200.f), a.side_inv_s2, a.side_kappa);
+              const float c1 = fmaf(fmaxf(__log2f(v1), -200.f), a.side_inv_s2, a.side_kappa);
+              a0 = fmaf(rh * v0, c0, a0);
+              a1 = fmaf(rh * v1, c1, a1);
             }
             __syncwarp();
+            if (lane == 0) mbar_arrive_local(bar_rdone + 8 * side_stage);
+            float* red = side_red + (kb & 1) * NUM_EPI_WARPS * 64;
+            reinterpret_cast<float2*>(red + ew * 64)[lane] = make_float2(a0, a1);
+            epi_bar_sync();
+            if (ew < 2) {
+              float t = 0.f;
+#pragma unroll
+              for (int k = 0; k < NUM_EPI_WARPS; ++k) t += red[k * 64 + ew * 32 + lane];
+              atomicAdd(a.rsum + (int64_t)kb * BK + ew * 32 + lane, t);
+            }
+            if (++side_stage == STAGES) { side_stage = 0; side_phase ^= 1; }
           }
-        } else if (MODE == MODE_DW || (MODE == MODE_DWF && a.layout == MH_LAYOUT_CD)) {
+        }
+        mbar_wait(bar_tfull + 8 * buf, bphase);
+        tc_fence_after();
+        chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
+          float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + cbase + c * 32;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            reinterpret_cast<uint4*>(dst)[k] = make_uint4(cur[4 * k], cur[4 * k + 1], cur[4 * k + 2], cur[4 * k + 3]);
+        }, release);
+      } else {
+        // ---- DW: this thread owns class `row` and 128 of the tile's 256 d columns ----
+        const bool raw = a.raw_dw != 0;
+        const bool ok = raw || row < a.C;
+        float rj = 0.f, coef = 1.f;
+        if (!raw && row < a.C) { rj = a.rsum[row]; coef = a.gscal[0] * a.inv_norm[row]; }
+        if (!raw && row >= a.C) coef = 0.f;
+        const __nv_bfloat16* wrow = a.w_hat + row * MH_D + w.n0 + cbase;          // rows >= C of w_hat are zero
+        const int rows_ok = raw ? 32 : (int)max((int64_t)0, min((int64_t)32, a.C - ((int64_t)w.m0 + q * 32)));
+        const int64_t opitch = raw ? (int64_t)MH_D : a.ld;
+        mbar_wait(bar_tfull + 8 * buf, bphase);
+        tc_fence_after();
+        chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
           float o[32];
-          if (MODE == MODE_DWF) {
-            const uint4* wsrc = reinterpret_cast<const uint4*>(a.w_hat + row * MH_D + w.n0 + col0);
+          if (raw) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(cur[k]);
+          } else {
+            const uint4* wsrc = reinterpret_cast<const uint4*>(wrow + c * 32);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-              uint4 wq = dwf_ok ? __ldg(wsrc + k4) : make_uint4(0u, 0u, 0u, 0u);
+              const uint4 wq = __ldg(wsrc + k4);
               const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
                 const int k = k4 * 8 + e * 2;
-                o[k] = (__uint_as_float(cur[k]) - wf.x * dwf_rj) * dwf_coef;
-                o[k + 1] = (__uint_as_float(cur[k + 1]) - wf.y * dwf_rj) * dwf_coef;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(cur[k]);
-          }
-          float4* dst = reinterpret_cast<float4*>(stg + lane * STG_ROW_BYTES + (c & 1) * 128);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-          if (c & 1) {
-            // two chunks (64 fp32 columns = 256 B per row) staged: write them out as full 128 B lines,
-            // 16 lanes per row, 2 rows per store instruction
-            __syncwarp();
-            const int64_t opitch = (MODE == MODE_DWF) ? a.ld : (int64_t)MH_D;
-            const int64_t rbase = (int64_t)w.m0 + q * 32;
-            float* obase = a.out + rbase * opitch + w.n0 + cbase + (c - 1) * 32;
-#pragma unroll
-            for (int i2 = 0; i2 < 16; ++i2) {
-              const int rr = 2 * i2 + (lane >> 4);
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * STG_ROW_BYTES + (lane & 15) * 16);
-              if (MODE == MODE_DW || rbase + rr < a.C)
-                *reinterpret_cast<uint4*>(obase + (int64_t)rr * opitch + (lane & 15) * 4) = val;
-            }
-            __syncwarp();
-          }
-        } else if (MODE == MODE_DWF) {
-          // parameter layout [D, C]: for a fixed d the 32 lanes are 32 consecutive classes -> coalesced directly
-          const uint4* wsrc = reinterpret_cast<const uint4*>(a.w_hat + row * MH_D + w.n0 + col0);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            uint4 wq = dwf_ok ? __ldg(wsrc + k4) : make_uint4(0u, 0u, 0u, 0u);
-            const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
-              const int k = k4 * 8 + e * 2;
-              if (dwf_ok) {
-                a.out[(int64_t)(w.n0 + col0 + k) * a.ld + row] = (__uint_as_float(cur[k]) - wf.x * dwf_rj) * dwf_coef;
-                a.out[(int64_t)(w.n0 + col0 + k + 1) * a.ld + row] = (__uint_as_float(cur[k + 1]) - wf.y * dwf_rj) * dwf_coef;
+                o[k] = (__uint_as_float(cur[k]) - wf.x * rj) * coef;
+                o[k + 1] = (__uint_as_float(cur[k + 1]) - wf.y * rj) * coef;
               }
             }
           }
-        } else {
-          float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + w.n0 + col0;
+          if (raw || a.layout == MH_LAYOUT_CD) {
+            // stage [32 rows][32 fp32 = 128 B], then full-line stores: 8 lanes per row, 4 rows per instruction
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            reinterpret_cast<uint4*>(dst)[k] = make_uint4(cur[4 * k], cur[4 * k + 1], cur[4 * k + 2], cur[4 * k + 3]);
-        }
-        if (c + 1 < NCHUNK) tmem_ld_wait();
-      }
-      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTA2) mbar_arrive_cluster(bar_tempty + 8 * buf, 0); else mbar_arrive(bar_tempty + 8 * buf);
-      }
-      if (MODE == MODE_FWD) {
-        float* sp = a.stats_tiles + ((int64_t)w.n_tile * 2 + half) * MH_ST_PLANES * a.B_pad;
-        sp[MH_ST_M * a.B_pad + row] = acc.m;
-        sp[MH_ST_L * a.B_pad + row] = acc.l;
-        sp[MH_ST_CNT * a.B_pad + row] = (float)acc.cnt;
-        sp[MH_ST_EZ * a.B_pad + row] = (V == V_SPHERE) ? acc.ez : 0.f;
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) * 16)) =
+                  make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            __syncwarp();
+            float* obase = a.out + ((int64_t)w.m0 + q * 32) * opitch + w.n0 + cbase + c * 32;
+            flush_tile(stg, lane, reinterpret_cast<uint8_t*>(obase), opitch * 4, rows_ok);
+            __syncwarp();
+          } else if (ok) {
+            // parameter layout [D, C]: for a fixed d the 32 lanes are 32 consecutive classes -> coalesced directly
+#pragma unroll
+            for (int k = 0; k < 32; ++k) a.out[(int64_t)(w.n0 + cbase + c * 32 + k) * a.ld + row] = o[k];
+          }
+        }, release);
       }
     }
   }
   __syncwarp();
   tc_fence_before();
-  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: the peer's smem / TMEM stay valid until both are done
+  cluster_sync_all();                                     // the peer's smem / TMEM stay valid until both are done
   if (warp == 2) {
     tc_fence_after();
-    if (CTA2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -895,46 +944,31 @@ int num_sms() {
   return n;
 }
 
-// cta_group::2 is the default; MH_TC_CTA2=0 selects the single-CTA kernels (kept for A/B measurements).
-bool use_cta2() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MH_TC_CTA2");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-template <int MODE, int V, bool CTA2>
-int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
+template <int MODE, int V>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
   static bool attr_set = false;
-  constexpr int smem = mode_smem_bytes(MODE, CTA2);
+  constexpr int smem = mode_smem_bytes(MODE);
   if (!attr_set) {
-    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int units = CTA2 ? num_sms() / 2 : num_sms();
+  const int units = num_sms() / 2;
   // A-stationary kernels use a static schedule over exactly `units` pairs (pairs without work exit at once)
-  const int n = mode_astat(MODE, CTA2) ? units : (int)std::min<int64_t>(args.total_tiles, units);
+  const int n = mode_astat(MODE) ? units : (int)std::min<int64_t>(args.total_tiles, units);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(CTA2 ? 2 * n : n);
+  cfg.gridDim = dim3(2 * n);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel<MODE, V, CTA2>, ta, tb, args));
+  MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel<MODE, V>, ta, tb, args));
   return MH_OK;
-}
-
-template <int MODE, int V>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, bool cta2, cudaStream_t st) {
-  return cta2 ? launch_impl<MODE, V, true>(ta, tb, args, st) : launch_impl<MODE, V, false>(ta, tb, args, st);
 }
 
 int variant_of(const MhParams& p) {
@@ -946,14 +980,33 @@ int variant_of(const MhParams& p) {
 }
 
 template <int MODE>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, bool cta2, cudaStream_t st) {
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
   switch (variant_of(args.p)) {
-    case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, cta2, st);
-    case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, cta2, st);
-    case V_SPHERE: return launch<MODE, V_SPHERE>(ta, tb, args, cta2, st);
-    case V_MV: return launch<MODE, V_MV>(ta, tb, args, cta2, st);
-    default: return launch<MODE, V_CURR>(ta, tb, args, cta2, st);
+    case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, st);
+    case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, st);
+    case V_SPHERE:
+      if (MODE == MODE_FWDS) { mh_set_error("the forward stash is not available for SphereFace"); return MH_ERR_ARG; }
+      return launch<MODE == MODE_FWDS ? MODE_FWD : MODE, V_SPHERE>(ta, tb, args, st);
+    case V_MV: return launch<MODE, V_MV>(ta, tb, args, st);
+    default: return launch<MODE, V_CURR>(ta, tb, args, st);
   }
+}
+
+float family_umax(const MhParams& p) { return mh_family_umax(&p); }
+
+// A-stationary schedule parameters for m_tiles <= units row tiles (see StatIter).
+void make_sched(TcArgs& a, int units) {
+  a.sG = units / a.m_tiles;
+  a.sE = units - a.sG * a.m_tiles;
+  const int64_t wfix = (int64_t)a.sG * a.m_tiles;
+  a.n_fixed = a.sE == 0 ? a.n_tiles : (int)(((int64_t)a.n_tiles * wfix + (wfix + a.sE) / 2) / (wfix + a.sE));
+}
+
+int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
+  MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % BMT == 0, "B_pad must be a multiple of 256 for the tensor-core path");
+  MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % BN == 0, "C_pad must be a multiple of 256 for the tensor-core path");
+  MH_CHECK_ARG(C_pad < (1ll << 31) && B_pad < (1ll << 31) && (C_pad / 128) * B_pad < (1ll << 31), "dimension too large");
+  return MH_OK;
 }
 
 }  // namespace
@@ -961,19 +1014,21 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a
 // two statistics records per 256-wide class tile (one per 128-column epilogue half)
 extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { return 2 * ((C_pad + BN - 1) / BN); }
 
-static int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
-  MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % BM == 0, "B_pad must be a multiple of 128");
-  MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % BN == 0, "C_pad must be a multiple of 256 for the tensor-core path");
-  MH_CHECK_ARG(C_pad < (1ll << 31) && B_pad < (1ll << 31) && (C_pad / 128) * B_pad < (1ll << 31), "dimension too large");
-  return MH_OK;
+// Fixed-reference softmax (and with it the forward stash) is used when every possible non-target term
+// exp2(z log2e - ref), ref = s log2e umax - 102, is a normal fp32 AND bf16 number with head-room for the row sums and
+// for rho_i = s 2^(ref - lse): s log2e (umax + 1) <= 200, a fixed logit scale, and at least two classes per shard.
+extern "C" int mh_tc_fixref_ok(const mh_config* cfg_host, int64_t C) {
+  if (!cfg_host) return 0;
+  const MhParams p = mh_make_params(cfg_host);
+  if (p.scale_is_norm || C < 2 || !(p.s > 0.f)) return 0;
+  return (p.s * MH_LOG2E * (family_umax(p) + 1.f) <= 200.f) ? 1 : 0;
 }
 
-// A-stationary schedule parameters for m_tiles <= units row tiles (see StatIter).
-static void make_sched(TcArgs& a, int units) {
-  a.sG = units / a.m_tiles;
-  a.sE = units - a.sG * a.m_tiles;
-  const int64_t wfix = (int64_t)a.sG * a.m_tiles;
-  a.n_fixed = a.sE == 0 ? a.n_tiles : (int)(((int64_t)a.n_tiles * wfix + (wfix + a.sE) / 2) / (wfix + a.sE));
+// The forward stash additionally needs u = cos on every non-target column (no MV / Curricular re-weighting): the
+// backward recovers cos_ij from the stashed exponential for the projection term r_j.
+extern "C" int mh_tc_stash_ok(const mh_config* cfg_host, int64_t C) {
+  if (!mh_tc_fixref_ok(cfg_host, C)) return 0;
+  return mh_make_params(cfg_host).hard_kind == 0 ? 1 : 0;
 }
 
 // Test hook (host only, no device work): the (pair, m_tile, n_tile) triples of the A-stationary schedule in
@@ -996,46 +1051,52 @@ extern "C" int64_t mh_tc_schedule_tiles(int units, int m_tiles, int n_tiles, int
   return cnt;
 }
 
-// FWD / BWD_G launch.  cta2: A-stationary schedule; row tiles beyond `units` pairs go in further launches.
+// FWD / FWDS / BWD_G launch: A-stationary schedule; row tiles beyond `units` pairs go in further launches.
 template <int MODE>
 static int launch_s_tiles(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
                           int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
-                          const float* state, const float* lse2, float* stats_tiles, void* G_bf16, float* r_colsum,
+                          const float* state, const float* lse2, float* stats_tiles, void* bc_bf16, float* r_colsum,
                           cudaStream_t st) {
-  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
-  const int bmt = cta2 ? 2 * BM : BM;
-  const int units = cta2 ? num_sms() / 2 : num_sms();
+  const int units = num_sms() / 2;
   CUtensorMap tb;
-  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, cta2 ? BN / 2 : BN)) return e;
-  const int64_t rows_per_launch = cta2 ? (int64_t)units * bmt : B_pad;
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN / 2)) return e;
+  const int64_t rows_per_launch = (int64_t)units * BMT;
   for (int64_t r0 = 0; r0 < B_pad; r0 += rows_per_launch) {
     const int64_t rows = std::min(rows_per_launch, B_pad - r0);
     if (r0 >= B) break;                                               // only padding rows left
     CUtensorMap ta;
     if (int e = make_tmap(&ta, (const __nv_bfloat16*)x_hat_bf16 + r0 * MH_D, rows, MH_D, BM)) return e;
     TcArgs a{};
-    a.m_tiles = (int)(rows / bmt); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
+    a.m_tiles = (int)(rows / BMT); a.n_tiles = (int)(C_pad / BN); a.n_split = 1;
     a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
     a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
-    if (cta2) make_sched(a, units);
+    make_sched(a, units);
     a.p = mh_make_params(cfg_host);
+    a.fixref = mh_tc_fixref_ok(cfg_host, C);
+    a.umax = family_umax(a.p);
     a.B = B - r0; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
     a.rowp = rowp + r0; a.ldp = ldp; a.label_local = label_local + r0; a.state = state;
     a.lse2 = lse2 ? lse2 + r0 : nullptr;
     a.stats_tiles = stats_tiles ? stats_tiles + r0 : nullptr;
-    a.G = G_bf16 ? (__nv_bfloat16*)G_bf16 + r0 * 128 : nullptr;
+    a.G = bc_bf16 ? (__nv_bfloat16*)bc_bf16 + r0 * 128 : nullptr;
     a.rsum = r_colsum;
-    if (int e = launch_variant<MODE>(ta, tb, a, cta2, st)) return e;
+    if (int e = launch_variant<MODE>(ta, tb, a, st)) return e;
   }
   return MH_OK;
 }
 
 extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                              const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
-                             const int32_t* label_local, const float* state, float* stats_tiles, void* stream) {
+                             const int32_t* label_local, const float* state, float* stats_tiles, void* stash_bf16,
+                             void* stream) {
   MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && stats_tiles, "null pointer");
   if (int e = check_common(B, B_pad, C, C_pad)) return e;
   MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
+  if (stash_bf16) {
+    MH_CHECK_ARG(mh_tc_stash_ok(cfg_host, C), "head not eligible for the forward stash (see mh_tc_stash_ok)");
+    return launch_s_tiles<MODE_FWDS>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+                                     nullptr, stats_tiles, stash_bf16, nullptr, (cudaStream_t)stream);
+  }
   return launch_s_tiles<MODE_FWD>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
                                   nullptr, stats_tiles, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -1052,13 +1113,13 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
                                     lse2, nullptr, G_bf16, r_colsum, (cudaStream_t)stream);
 }
 
-extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
-                                 int* n_split_host, void* stream) {
-  MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
-  const bool cta2 = use_cta2() && (B_pad % (2 * BM) == 0);
-  const int m_tiles = (int)(B_pad / (cta2 ? 2 * BM : BM));
+static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
+                               int* n_split_host, const float* rho, float kappa, float inv_s2, float* r_colsum,
+                               void* stream) {
+  MH_CHECK_ARG(B_pad > 0 && B_pad % BMT == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
+  const int m_tiles = (int)(B_pad / BMT);
   const int kb_total = (int)(C_pad / BK);
-  int n_split = std::max(1, (cta2 ? num_sms() / 2 : num_sms()) / m_tiles);
+  int n_split = std::max(1, (num_sms() / 2) / m_tiles);
   n_split = std::min(n_split, kb_total);
   int per = (kb_total + n_split - 1) / n_split;
   n_split = (kb_total + per - 1) / per;                 // no empty splits
@@ -1074,24 +1135,50 @@ extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pa
   a.total_tiles = (int64_t)m_tiles * n_split;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
-  return launch<MODE_DX, V_NONE>(ta, tb, a, cta2, (cudaStream_t)stream);
+  a.rho = rho; a.side_kappa = kappa; a.side_inv_s2 = inv_s2; a.rsum = r_colsum;
+  if (rho) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
+  return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
+}
+
+extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
+                                 int* n_split_host, void* stream) {
+  return tc_backward_dx_impl(G_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, nullptr, 0.f, 0.f, nullptr, stream);
+}
+
+extern "C" int mh_tc_backward_dx_stash(const mh_config* cfg_host, const void* stash_bf16, int64_t B_pad, int64_t C,
+                                       int64_t C_pad, const void* w_hat_bf16, const float* rho, float* out,
+                                       float* r_colsum, int* n_split_host, void* stream) {
+  MH_CHECK_ARG(cfg_host, "null pointer");
+  MH_CHECK_ARG(!out || (rho && r_colsum), "null pointer");
+  MH_CHECK_ARG(mh_tc_stash_ok(cfg_host, C), "head not eligible for the stash backward (see mh_tc_stash_ok)");
+  const MhParams p = mh_make_params(cfg_host);
+  const float s2 = p.s * MH_LOG2E;
+  return tc_backward_dx_impl(stash_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, out ? rho : nullptr,
+                             (s2 * family_umax(p) - 102.f) / s2, 1.f / s2, r_colsum, stream);
+}
+
+static int launch_dw(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_bf16, TcArgs& a,
+                     cudaStream_t st) {
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&ta, G_bf16, (C_pad / 128) * B_pad, 128, 64)) return e;    // A = G^T (class-tiled G), MN-major boxes
+  if (int e = make_tmap(&tb, x_bf16, B_pad, MH_D, 64)) return e;                   // B = x^, MN-major boxes [64 rows][64 d]
+  a.m_tiles = (int)(C_pad / BMT); a.n_tiles = 2; a.n_split = 1;
+  a.k_blocks_total = (int)(B_pad / BK); a.k_blocks_per_split = a.k_blocks_total;
+  a.total_tiles = (int64_t)a.m_tiles * 2;
+  a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C;
+  a.out_split_stride = 0;
+  return launch<MODE_DW, V_NONE>(ta, tb, a, st);
 }
 
 extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
                                  float* dw_hat, void* stream) {
   MH_CHECK_ARG(G_bf16 && x_hat_bf16 && dw_hat, "null pointer");
   MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
-  CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, G_bf16, (C_pad / 128) * B_pad, 128, 64)) return e;    // A = G^T (class-tiled G), MN-major boxes
-  if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;       // B = x^,  MN-major boxes [64 rows][64 d]
-  const bool cta2 = use_cta2();                                     // C_pad is always a multiple of 256
+  MH_CHECK_ARG(((uintptr_t)dw_hat & 15) == 0, "dw_hat must be 16-byte aligned");
   TcArgs a{};
-  a.m_tiles = (int)(C_pad / (cta2 ? 2 * BM : BM)); a.n_tiles = 2; a.n_split = 1;
-  a.k_blocks_total = (int)(B_pad / BK); a.k_blocks_per_split = a.k_blocks_total;
-  a.total_tiles = (int64_t)a.m_tiles * 2;
-  a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
-  a.out = dw_hat; a.out_split_stride = 0;
-  return launch<MODE_DW, V_NONE>(ta, tb, a, cta2, (cudaStream_t)stream);
+  a.out = dw_hat; a.raw_dw = 1; a.layout = MH_LAYOUT_CD; a.ld = MH_D;
+  a.w_hat = (const __nv_bfloat16*)x_hat_bf16;            // never read in raw mode; any valid pointer
+  return launch_dw(G_bf16, B_pad, C_pad, C_pad, x_hat_bf16, a, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
@@ -1101,17 +1188,9 @@ extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_
   MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0 && C > 0 && C <= C_pad, "bad padded shape");
   MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
   MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)dW & 15) == 0), "CD dW must be 16-byte aligned");
-  CUtensorMap ta, tb;
-  if (int e = make_tmap(&ta, G_bf16, (C_pad / 128) * B_pad, 128, 64)) return e;    // class-tiled G
-  if (int e = make_tmap(&tb, x_hat_bf16, B_pad, MH_D, 64)) return e;
-  const bool cta2 = use_cta2();
   TcArgs a{};
-  a.m_tiles = (int)(C_pad / (cta2 ? 2 * BM : BM)); a.n_tiles = 2; a.n_split = 1;
-  a.k_blocks_total = (int)(B_pad / BK); a.k_blocks_per_split = a.k_blocks_total;
-  a.total_tiles = (int64_t)a.m_tiles * 2;
-  a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C;
-  a.out = dW; a.out_split_stride = 0;
-  a.rsum = const_cast<float*>(r_colsum); a.w_hat = (const __nv_bfloat16*)w_hat_bf16; a.inv_norm = inv_norm;
-  a.gscal = gscal; a.layout = layout; a.ld = ld;
-  return launch<MODE_DWF, V_NONE>(ta, tb, a, cta2, (cudaStream_t)stream);
+  a.out = dW; a.raw_dw = 0; a.layout = layout; a.ld = ld;
+  a.w_hat = (const __nv_bfloat16*)w_hat_bf16; a.inv_norm = inv_norm; a.gscal = gscal;
+  a.rsum = const_cast<float*>(r_colsum);
+  return launch_dw(G_bf16, B_pad, C, C_pad, x_hat_bf16, a, (cudaStream_t)stream);
 }

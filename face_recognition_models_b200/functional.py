@@ -2,8 +2,13 @@
 
 Two execution paths, both CUDA only (there is no CPU / PyTorch fallback):
 
-* ``tc``    - bf16 tensor-core path (tcgen05 + TMEM + TMA).  Forward never materialises B x C;
-              backward recomputes the logit tiles and keeps only G = (P-Y) dz/dcos in bf16.
+* ``tc``    - bf16 tensor-core path (tcgen05 + TMEM + TMA).  A forward that needs no gradient never
+              materialises B x C.  For training there are two backward modes:
+              ``recompute`` - backward recomputes the logit tiles and keeps only G = (P-Y) dz/dcos in bf16;
+              ``stash``     - the forward additionally writes the unnormalised probabilities
+                              E' = exp2(z - ref) du/dcos in bf16 (fixed softmax reference), and the backward
+                              runs only the two gradient GEMMs (3 instead of 4 GEMM passes per step).
+              ``auto`` (default) = stash whenever ``mh_tc_fixref_ok`` holds for the head, else recompute.
 * ``exact`` - fp32 SIMT path that materialises the cosine matrix (small C: fp32-tolerance mode,
               and the compat mode returning the reference's 4-tuple).
 
@@ -14,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -73,6 +79,18 @@ class HeadEngine:
             setattr(self.cfg, k, v)
         self._ws: Dict[str, torch.Tensor] = {}
         self._gen = 0
+        # "auto" | "stash" | "recompute"; MH_BACKWARD in the environment overrides (A/B measurements)
+        self.backward_mode = os.environ.get("MH_BACKWARD", "auto")
+
+    def stash_ok(self) -> bool:
+        """True when the forward may stash E' for the backward (fixed-reference softmax applies)."""
+        if self.mode != "tc" or self.backward_mode == "recompute":
+            return False
+        ok = bool(L.load().mh_tc_stash_ok(C.byref(self.cfg), self.C))
+        if self.backward_mode == "stash" and not ok:
+            raise L.MarginHeadError("backward_mode='stash' needs a head that passes mh_tc_stash_ok (fixed scale with "
+                                    "s*log2(e)*2 <= 200, no hard-negative re-weighting)")
+        return ok
 
     # -- workspace ------------------------------------------------------------------------------
     def _buf(self, name: str, shape, dtype, device, zero: bool = False) -> torch.Tensor:
@@ -88,8 +106,10 @@ class HeadEngine:
 
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, state: torch.Tensor,
-                margins: Optional[torch.Tensor], update_state: bool = True, want_dense: bool = False):
+                margins: Optional[torch.Tensor], update_state: bool = True, want_dense: bool = False,
+                want_grad: bool = False):
         """Runs prologues + fused forward.  x is the (already gathered) global batch [B, 512].
+        want_grad: a backward will follow, so the forward may stash E' (see the module docstring).
 
         Returns a context dict with every tensor the backward needs plus the user-visible outputs.
         """
@@ -149,7 +169,7 @@ class HeadEngine:
                1 if update_state else 0, _ptr(rowp), B_pad, st)
 
         stats = self._buf("stats", (L.ST_PLANES, B_pad), torch.float32, dev)
-        S = pre = logits = None
+        S = pre = logits = stash = None
         if exact:
             S = self._buf("S", (B, Cn), torch.float32, dev)
             # S = x_hat32 [B,512] . w_hat32^T  (w_hat32 is [C,512]: B operand strides (1, 512))
@@ -163,8 +183,10 @@ class HeadEngine:
             n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
             stats_tiles = self._buf("stats_tiles", (n_tiles, L.ST_PLANES, B_pad), torch.float32, dev)
             scratch = self._buf("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev)
+            if want_grad and self.stash_ok():
+                stash = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
             L.call("mh_tc_forward", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_hat), Cn, C_pad, _ptr(rowp), B_pad,
-                   _ptr(label_local), _ptr(state), _ptr(stats_tiles), st)
+                   _ptr(label_local), _ptr(state), _ptr(stats_tiles), _ptr(stash), st)
             L.call("mh_merge_stats", _ptr(stats_tiles), n_tiles, B, B_pad, _ptr(scratch), _ptr(stats), st)
 
         if self.shard.world > 1:
@@ -180,7 +202,7 @@ class HeadEngine:
         return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=w_hat, w_hat32=w_hat32, inv_norm=inv_norm,
                     x_hat=x_hat, x_hat32=x_hat32, xnorm=xnorm, label_local=label_local, rowp=rowp, rowout=rowout,
                     scalars=scalars, S=S, pre=pre, logits=logits, exact=exact, gen=self._gen, state=state,
-                    W_shape=tuple(W.shape), ld=ld)
+                    W_shape=tuple(W.shape), ld=ld, stash=stash)
 
     # -- backward of the fused loss ------------------------------------------------------------------
     def backward(self, ctx: Dict, g_loss: torch.Tensor, g_lossg: Optional[torch.Tensor],
@@ -203,22 +225,47 @@ class HeadEngine:
             L.call("mh_dense_backward_dc", C.byref(self.cfg), _ptr(S), Cn, B, Cn, _ptr(rowp), B_pad,
                    _ptr(ctx["label_local"]), _ptr(state), _ptr(lse2), _ptr(None), _ptr(None), _ptr(None), st)
             return self._exact_grads(ctx, S, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]], need_dx, need_dw)
-        G = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
-        rsum = self._buf("r_colsum", (C_pad,), torch.float32, dev) if need_dw else None
-        L.call("mh_tc_backward_g", C.byref(self.cfg), _ptr(ctx["x_hat"]), B, B_pad, _ptr(ctx["w_hat"]), Cn, C_pad,
-               _ptr(rowp), B_pad, _ptr(ctx["label_local"]), _ptr(state), _ptr(lse2), _ptr(G), _ptr(rsum), st)
+        w_hat, x_hat, label_local = ctx["w_hat"], ctx["x_hat"], ctx["label_local"]
+        stash = ctx.get("stash")
+        rsum = self._buf("r_colsum", (C_pad,), torch.float32, dev)
+        ns = C.c_int(0)
+        L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), st)
+        n_split = ns.value
+        split_stride = B_pad * L.D
         dx = dW = None
-        if need_dx:
-            ns = C.c_int(0)
-            L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(ctx["w_hat"]), _ptr(None), C.byref(ns), st)
-            n_split = ns.value
+        if stash is not None:
+            # stash mode: G_ij = rho_i E'_ij off the target column; the target column is a sparse fp32 term.
+            # The dx GEMM always runs: its idle epilogue warps also produce r_colsum for the dW projection.
+            G = stash
+            xs = self._buf("xs", (B_pad, L.D), torch.bfloat16, dev)
+            rho = self._buf("rho", (B_pad,), torch.float32, dev)
+            gty = self._buf("gty", (B_pad,), torch.float32, dev)
+            L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
+                   _ptr(xs), _ptr(rho), _ptr(gty), st)
             part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
-            L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(ctx["w_hat"]), _ptr(part), C.byref(ns), st)
-            dx = self._finish_dx(ctx, part, n_split, B_pad * L.D, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
+            L.call("mh_tc_backward_dx_stash", C.byref(self.cfg), _ptr(G), B_pad, Cn, C_pad, _ptr(w_hat), _ptr(rho), _ptr(part),
+                   _ptr(rsum), C.byref(ns), st)
+            if need_dx:
+                full = self._buf("dxhat_full", (1, B_pad, L.D), torch.float32, dev)
+                L.call("mh_stash_dx_combine", _ptr(part), n_split, split_stride, _ptr(rho), _ptr(gty), _ptr(label_local),
+                       _ptr(w_hat), B, _ptr(full), st)
+                dx = self._finish_dx(ctx, full, 1, split_stride, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
+        else:
+            G = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
+            L.call("mh_tc_backward_g", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_hat), Cn, C_pad,
+                   _ptr(rowp), B_pad, _ptr(label_local), _ptr(state), _ptr(lse2), _ptr(G), _ptr(rsum if need_dw else None), st)
+            xs = x_hat
+            if need_dx:
+                part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
+                L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(w_hat), _ptr(part), C.byref(ns), st)
+                dx = self._finish_dx(ctx, part, n_split, split_stride, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
         if need_dw:
             dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
-            L.call("mh_tc_backward_dw_fused", _ptr(G), B_pad, Cn, C_pad, _ptr(ctx["x_hat"]), _ptr(ctx["w_hat"]),
-                   _ptr(ctx["inv_norm"]), _ptr(rsum), _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], st)
+            L.call("mh_tc_backward_dw_fused", _ptr(G), B_pad, Cn, C_pad, _ptr(xs), _ptr(w_hat), _ptr(ctx["inv_norm"]),
+                   _ptr(rsum), _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], st)
+            if stash is not None:
+                L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
+                       _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
         return dx, dW
 
     def _finish_dx(self, ctx, part, n_split, split_stride, gscal, aux0, aux1):
@@ -291,8 +338,10 @@ class FusedMarginLossFn(torch.autograd.Function):
     """loss_id, loss_g, acc1, acc5, norms = f(x, W, labels).  Only loss_id / loss_g are differentiable."""
 
     @staticmethod
-    def forward(ctx, x, W, labels, engine: HeadEngine, state, margins, update_state):
-        c = engine.forward(x, W, labels, state, margins, update_state=update_state)
+    def forward(ctx, x, W, labels, engine: HeadEngine, state, margins, update_state, grad_enabled=True):
+        # grad_enabled = torch.is_grad_enabled() at the call site (always False inside Function.forward)
+        c = engine.forward(x, W, labels, state, margins, update_state=update_state,
+                           want_grad=bool(grad_enabled and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])))
         ctx.engine = engine
         ctx.c = c
         ctx.x_dtype = x.dtype
@@ -312,7 +361,7 @@ class FusedMarginLossFn(torch.autograd.Function):
             g_loss = torch.zeros((), device=ctx.c["x_hat"].device)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx, dW = eng.backward(ctx.c, g_loss, g_lossg, need_dx, need_dw)
-        return dx, dW, None, None, None, None, None
+        return dx, dW, None, None, None, None, None, None
 
 
 class DenseMarginLogitsFn(torch.autograd.Function):

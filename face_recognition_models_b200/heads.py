@@ -55,6 +55,16 @@ class _MarginHeadBase(nn.Module):
         assert v in ("tc", "exact")
         self._engine.mode = v
 
+    # backward of the tensor-core path: "auto" (stash when the head allows it), "stash" or "recompute"
+    @property
+    def backward_mode(self) -> str:
+        return self._engine.backward_mode
+
+    @backward_mode.setter
+    def backward_mode(self, v: str):
+        assert v in ("auto", "stash", "recompute")
+        self._engine.backward_mode = v
+
     def _param(self) -> torch.Tensor:
         return getattr(self, self.param_name)
 
@@ -86,7 +96,7 @@ class _MarginHeadBase(nn.Module):
         margins = self._sample_margins(feats, labels)
         self._push_state()
         out = FusedMarginLossFn.apply(feats, self._param(), labels, self._engine, self._mh_state, margins,
-                                      self.training or True)
+                                      self.training or True, torch.is_grad_enabled())
         self._pull_state()
         return FusedOutput(*out)
 

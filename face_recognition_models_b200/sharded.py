@@ -85,12 +85,13 @@ class ShardComm:
 
 class _ShardedFusedLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, W_local, labels_local, head, margins_local):
+    def forward(ctx, x_local, W_local, labels_local, head, margins_local, grad_enabled=True):
         comm: ShardComm = head.comm
         x_g = comm.gather_rows(x_local.contiguous())
         y_g = comm.gather_rows(labels_local.contiguous().to(torch.int64))
         margins_g = comm.gather_rows(margins_local.contiguous()) if margins_local is not None else None
-        c = head.engine.forward(x_g, W_local, y_g, head._mh_state, margins_g, update_state=True)
+        c = head.engine.forward(x_g, W_local, y_g, head._mh_state, margins_g, update_state=True,
+                                want_grad=bool(grad_enabled and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])))
         ctx.head = head
         ctx.c = c
         ctx.B_local = x_local.shape[0]
@@ -109,7 +110,7 @@ class _ShardedFusedLossFn(torch.autograd.Function):
         dx, dW = head.engine.backward(ctx.c, g_loss, g_lossg, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         if dx is not None and head.dx_scale != 1.0:
             dx = dx * head.dx_scale
-        return dx, dW, None, None, None
+        return dx, dW, None, None, None, None
 
 
 class ShardedMarginHead(nn.Module):
@@ -150,7 +151,7 @@ class ShardedMarginHead(nn.Module):
         self.local._pre_forward(feats)
         margins = self.local._sample_margins(feats, labels)
         self.local._push_state()
-        out = _ShardedFusedLossFn.apply(feats, self.local._param(), labels, self, margins)
+        out = _ShardedFusedLossFn.apply(feats, self.local._param(), labels, self, margins, torch.is_grad_enabled())
         self.local._pull_state()
         return FusedOutput(*out)
 

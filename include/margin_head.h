@@ -150,18 +150,30 @@ int64_t mh_fwd_num_tiles(int64_t C_pad);
  * int32 triples in per-pair execution order and returns the total number of tiles scheduled (or a negative status). */
 int64_t mh_tc_schedule_tiles(int units, int m_tiles, int n_tiles, int32_t* out, int64_t cap);
 
-/* Fused cos-GEMM + margin + online softmax (replaces F.linear/torch.mm at criterion.py:65,176,267,
+/* 1 when the head can use the fixed-reference softmax: fixed logit scale s with s*log2(e)*(umax+1) <= 200 (umax =
+ * largest possible z/s on a non-target column: 1, MV 2w-1, Curricular 2) and C >= 2.  Then every term
+ * exp2(z*log2e - ref), ref = s*log2e*umax - 102, is a normal fp32/bf16 number, no running max is needed and the row
+ * sums cannot overflow.  SphereFace (scale = |x|) and large s use the online-max forward. */
+int mh_tc_fixref_ok(const mh_config* cfg_host, int64_t C);
+/* 1 when the forward may stash for the backward: mh_tc_fixref_ok and no hard-negative re-weighting (MV-Softmax,
+ * CurricularFace), because the backward recovers cos_ij from the stashed exponential.  Otherwise: recompute backward. */
+int mh_tc_stash_ok(const mh_config* cfg_host, int64_t C);
+
+/* Fused cos-GEMM + margin + softmax statistics (replaces F.linear/torch.mm at criterion.py:65,176,267,
  * 408,545,868,990,1100,1256, the elementwise margin passes and nn.CrossEntropyLoss's log-softmax,
- * model_utils.py:179).  stats_tiles is [num_tiles, MH_ST_PLANES, B_pad]; nothing of size B x C is
- * written. */
+ * model_utils.py:179).  stats_tiles is [num_tiles, MH_ST_PLANES, B_pad].  B_pad must be a multiple of 256.
+ * stash_bf16 == NULL: nothing of size B x C is written (inference / recompute-backward mode).
+ * stash_bf16 != NULL (training, needs mh_tc_stash_ok): additionally writes E'_ij = exp2(z_ij*log2e - ref_i) * du_ij/dcos
+ * as bf16, class-tiled [C_pad/128][B_pad][128] (element (row i, class j) at ((j/128)*B_pad + i)*128 + j%128), with the
+ * target column, padded classes and rows >= B set to 0.  The backward then needs no logit recompute:
+ * G_ij = rho_i * E'_ij for j != y_i (see mh_stash_prep). */
 int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                   const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
-                  const int32_t* label_local, const float* state, float* stats_tiles, void* stream);
+                  const int32_t* label_local, const float* state, float* stats_tiles, void* stash_bf16, void* stream);
 
-/* Backward step 1: recompute the logit tiles and write G = (P - Y) * dz/dcos as bf16 (the only B x C object of the
- * path; never the logits).  G is stored CLASS-TILED: [C_pad/128][B_pad][128], i.e. element (row i, class j) lives at
- * ((j/128)*B_pad + i)*128 + j%128, so each 128-class slab of all rows is one contiguous block (DRAM-page friendly for
- * both consumers); mh_tc_backward_dx / _dw / _dw_fused expect this layout.  lse2 = rowout plane MH_RO_LSE2.
+/* Recompute backward, step 1: recompute the logit tiles and write G = (P - Y) * dz/dcos as bf16 (never the logits), in the
+ * same class-tiled layout as the stash, so each 128-class slab of all rows is one contiguous block (DRAM-page friendly
+ * for both consumers); mh_tc_backward_dx / _dw / _dw_fused expect this layout.  lse2 = rowout plane MH_RO_LSE2.
  * r_colsum [C_pad] (may be NULL) receives r_j = sum_i G_ij * cos_ij = w^_j . dw^_j, the projection term of
  * the normalise-backward of W; it is zeroed (stream-ordered) before the kernel accumulates into it. */
 int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
@@ -169,22 +181,49 @@ int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t 
                      const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
                      float* r_colsum, void* stream);
 
-/* Backward step 2: dx_hat partials = G . w_hat, split over the class dimension.
+/* dx_hat partials = G . w_hat, split over the class dimension.
  * Returns the number of splits through *n_split_host (call with out == NULL to query).
  * out is [n_split, B_pad, 512] fp32. */
 int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16,
                       float* out, int* n_split_host, void* stream);
 
-/* Backward step 3: dw_hat = G^T . x_hat, [C_pad, 512] fp32 (unscaled). */
+/* Stash mode: the same GEMM on the stash E' (out = E' . w_hat; scale the rows by rho afterwards, mh_stash_dx_combine).
+ * While the tensor cores run, the kernel's idle epilogue warps re-read every E' tile from shared memory and accumulate
+ * r_colsum[j] = sum_i rho_i * E'_ij * cos_ij (zeroed first, stream-ordered), with cos_ij = log2(E'_ij)/(s log2e) + ref/(s log2e)
+ * recovered from the stash itself: the non-target part of the projection term w^_j . dw^_j that mh_tc_backward_dw_fused
+ * needs (the target column's part is added by mh_stash_dw_target). */
+int mh_tc_backward_dx_stash(const mh_config* cfg_host, const void* stash_bf16, int64_t B_pad, int64_t C, int64_t C_pad,
+                            const void* w_hat_bf16, const float* rho, float* out, float* r_colsum, int* n_split_host,
+                            void* stream);
+
+/* dw_hat = G^T . x_hat, [C_pad, 512] fp32 (unscaled, unprojected). */
 int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
                       float* dw_hat, void* stream);
 
-/* Backward step 3, fused with the normalise-backward of W (autograd of F.normalize(self.weight), criterion.py:264):
+/* dw_hat = G^T . x_hat fused with the normalise-backward of W (autograd of F.normalize(self.weight), criterion.py:264):
  * dW_j = gscal[0] * (dw^_j - w^_j * r_j) / |w_j| written straight into the parameter layout (ld = row pitch);
- * replaces mh_tc_backward_dw + mh_norm_backward_w and their 4*C*d-byte dw_hat round trip. */
+ * replaces mh_tc_backward_dw + mh_norm_backward_w and their 4*C*d-byte dw_hat round trip.  x_hat_bf16 is x^ (recompute
+ * mode, G from mh_tc_backward_g) or the rho-scaled rows of mh_stash_prep (stash mode, G = the stash). */
 int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
                             const void* w_hat_bf16, const float* inv_norm, const float* r_colsum,
                             const float* gscal, int layout, float* dW, int64_t ld, void* stream);
+
+/* ---- stash backward: O(B*d) helpers (see mh_tc_forward's stash) -------------------------------------- */
+
+/* rho_i = scale_i * 2^(ref_i - lse2_i), gty_i = G_{i,y_i} = (P_iy - 1) * dz_iy/dcos (rowout AUX0 * rowp DZT) and
+ * xs = bf16(rho_i * x^_i) [B_pad, 512] (rows >= B zero): the B operand of mh_tc_backward_dw_fused in stash mode. */
+int mh_stash_prep(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
+                  const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty, void* stream);
+
+/* dxhat [B, 512] = rho_i * sum_splits dxhat_part + gty_i * w^_{y_i} (target term only where label_local >= 0). */
+int mh_stash_dx_combine(const float* dxhat_part, int n_split, int64_t split_stride, const float* rho, const float* gty,
+                        const int32_t* label_local, const void* w_hat_bf16, int64_t B, float* dxhat, void* stream);
+
+/* Adds the target-column term to dW after mh_tc_backward_dw_fused ran on the stash:
+ * dW_j += gscal[0]/|w_j| * (delta_j - w^_j (w^_j . delta_j)), delta_j = sum_{i: y_i = j} gty_i x^_i.  Deterministic. */
+int mh_stash_dw_target(const float* gty, const int32_t* label_local, const float* x_hat32, const void* w_hat_bf16,
+                       const float* inv_norm, const float* gscal, int64_t B, int layout, float* dW, int64_t ld,
+                       void* stream);
 
 /* ---- exact fp32 path (SIMT; materialises S = x^ w^T [B, C]; small C, tests, compat mode) ------- */
 

@@ -154,7 +154,7 @@ def stage_tcgemm():
     pkg, L, _ptr, _stream, mo = _imports()
     dev = "cuda"
     torch.manual_seed(0)
-    for (B_pad, C_pad) in ((128, 256), (256, 1024), (1024, 4096)):
+    for (B_pad, C_pad) in ((256, 256), (256, 1024), (1024, 4096)):
         G = (torch.randn(B_pad, C_pad, device=dev) * 0.5).to(torch.bfloat16)
         wh = (torch.randn(C_pad, 512, device=dev) * 0.1).to(torch.bfloat16)
         xh = (torch.randn(B_pad, 512, device=dev) * 0.1).to(torch.bfloat16)

@@ -119,6 +119,8 @@ PROFILE = None
 def _launches(name: str, args) -> int:
     if name == "mh_merge_stats":
         return 2 if int(args[1]) >= 256 else 1
+    if name == "mh_tc_forward":
+        return 2                      # statistics-identity fill + the tensor-core kernel
     if name == "mh_tc_backward_dx":
         return 0 if not getattr(args[4], "value", None) else 1
     if name == "mh_tc_backward_dx_stash":

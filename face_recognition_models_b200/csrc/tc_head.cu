@@ -35,7 +35,7 @@ constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int STG_WARP_BYTES = 32 * 128;          // output staging per epilogue warp: 32 rows x 128 B, XOR-swizzled
-constexpr int DX_SIDE_BYTES = 2 * NUM_EPI_WARPS * 64 * 4 + 128 * 4;   // DX r_j side pass: partial sums (x2) + rho of the rows
+constexpr int DX_SIDE_BYTES = 0;
 
 enum { MODE_FWD = 0, MODE_FWDS = 1, MODE_BWD_G = 2, MODE_DX = 3, MODE_DW = 4 };
 // A-stationary (FWD / FWDS / BWD_G): the pair's x^ tile (128 rows x 512 per CTA = 128 KB) stays resident in shared
@@ -77,6 +77,7 @@ struct TcArgs {
   float* rsum;                 // r_j [C_pad]: DX (stash) accumulates into it, DW fused reads it
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
+  int side_debug;              // experiment: 1 = loads + release only (no math)
   const __nv_bfloat16* w_hat;  // DW fused
   const float* inv_norm;       // DW fused
   const float* gscal;          // DW fused
@@ -135,6 +136,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float lg2(float x) {      // log2, no denormal fix-up: lg2(0) = -inf
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -588,8 +594,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t bar_afull = bar_full + 8 * (2 * MAX_STAGES + 5);   // AS: resident A landed
   const uint32_t bar_afree = bar_afull + 8;                         // AS: every MMA that read the resident A retired
   const uint32_t bar_rdone = bar_afree + 8;                         // DX side pass: [STAGES] the epilogue warps read the A tile
-  float* side_red = reinterpret_cast<float*>(stg_all);              // DX side pass: [2][8 warps][64]
-  float* side_rho = side_red + 2 * NUM_EPI_WARPS * 64;              // DX side pass: [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -721,6 +725,22 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint8_t* stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;      // this warp's staging tile
     uint32_t it = 0;
     uint32_t side_stage = 0, side_phase = 0;          // DX side pass: walks the smem stages like the producer
+    // A-stationary modes: the thread keeps its row for as long as the pair keeps its row tile, so the row terms are
+    // loaded once and the softmax statistics accumulate in registers across class tiles (one record per pair, row and
+    // column half instead of one per tile).
+    int res_m = -1, res_y = -1;
+    int64_t res_row = 0;
+    RowCtx rc{};
+    FwdAcc acc{-INFINITY, 0.f, 0.f, 0.f, 0};
+    auto flush_stats = [&]() {
+      if (MODE == MODE_FWD || MODE == MODE_FWDS) {
+        float* sp = a.stats_tiles + ((int64_t)pid * 2 + half) * MH_ST_PLANES * a.B_pad;
+        sp[MH_ST_M * a.B_pad + res_row] = acc.m;
+        sp[MH_ST_L * a.B_pad + res_row] = acc.l;
+        sp[MH_ST_CNT * a.B_pad + res_row] = (float)acc.cnt + acc.cntf;
+        sp[MH_ST_EZ * a.B_pad + res_row] = (V == V_SPHERE) ? acc.ez : 0.f;
+      }
+    };
     TileLoop<MODE> tl;
     tl.init(a, pid, npid);
     Work w;
@@ -738,23 +758,26 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       auto no_op = [&]() {};
 
       if (AS) {
-        RowCtx rc;
-        rc.valid = row < a.B;
-        rc.tcol = -1;
-        rc.scale = a.rowp[MH_RP_SCALE * a.ldp + row];
-        rc.scale2 = rc.scale * MH_LOG2E;
-        rc.thr = a.rowp[MH_RP_THR * a.ldp + row];
-        rc.t = a.rowp[MH_RP_T * a.ldp + row];
-        rc.zt2 = a.rowp[MH_RP_ZT * a.ldp + row] * MH_LOG2E;
-        rc.dzt = a.rowp[MH_RP_DZT * a.ldp + row];
-        rc.nref2 = 102.f - rc.scale2 * a.umax;
-        rc.ntbig = -rc.t * CNT_BIG;
-        const int32_t y = a.label_local[row];
-        if (y >= w.n0 && y < w.n0 + BN) rc.tcol = y - w.n0;
-        rc.lse2 = (MODE == MODE_BWD_G && rc.valid) ? a.lse2[row] : 0.f;
-        const int nvalid = (int)min((int64_t)BN, a.C - (int64_t)w.n0);   // valid class columns in this tile
         const bool fix = (MODE == MODE_FWDS) || (MODE == MODE_FWD && V != V_SPHERE && a.fixref);
-        FwdAcc acc{-INFINITY, 0.f, 0.f, 0.f, 0};
+        if (w.m_tile != res_m) {
+          // a new resident row tile: flush the statistics of the previous one, (re)load this thread's row terms
+          if (res_m >= 0) flush_stats();
+          res_m = w.m_tile; res_row = row;
+          rc.valid = row < a.B;
+          rc.scale = a.rowp[MH_RP_SCALE * a.ldp + row];
+          rc.scale2 = rc.scale * MH_LOG2E;
+          rc.thr = a.rowp[MH_RP_THR * a.ldp + row];
+          rc.t = a.rowp[MH_RP_T * a.ldp + row];
+          rc.zt2 = a.rowp[MH_RP_ZT * a.ldp + row] * MH_LOG2E;
+          rc.dzt = a.rowp[MH_RP_DZT * a.ldp + row];
+          rc.nref2 = 102.f - rc.scale2 * a.umax;
+          rc.ntbig = -rc.t * CNT_BIG;
+          rc.lse2 = (MODE == MODE_BWD_G && rc.valid) ? a.lse2[row] : 0.f;
+          res_y = a.label_local[row];
+          acc = FwdAcc{fix ? -rc.nref2 : -INFINITY, 0.f, 0.f, 0.f, 0};
+        }
+        rc.tcol = (res_y >= w.n0 && res_y < w.n0 + BN) ? res_y - w.n0 : -1;
+        const int nvalid = (int)min((int64_t)BN, a.C - (int64_t)w.n0);   // valid class columns in this tile
         mbar_wait(bar_tfull + 8 * buf, bphase);
         tc_fence_after();
         chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
@@ -785,50 +808,67 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
         }, release);
-        if (MODE == MODE_FWD || MODE == MODE_FWDS) {
-          float* sp = a.stats_tiles + ((int64_t)w.n_tile * 2 + half) * MH_ST_PLANES * a.B_pad;
-          sp[MH_ST_M * a.B_pad + row] = fix ? -rc.nref2 : acc.m;
-          sp[MH_ST_L * a.B_pad + row] = acc.l;
-          sp[MH_ST_CNT * a.B_pad + row] = (float)acc.cnt + acc.cntf;
-          sp[MH_ST_EZ * a.B_pad + row] = (V == V_SPHERE) ? acc.ez : 0.f;
-        }
       } else if (MODE == MODE_DX) {
         if (a.rho) {
           // ---- side pass (stash mode): r_j += sum_i rho_i E'_ij cos_ij over this CTA's 128 rows, k-block by k-block.
-          // An A tile is [128 rows][64 classes] (128 B rows, 16 B chunks XOR-swizzled with row & 7); it is read once its
-          // MMAs have retired (bar_empty) and handed back to the producer through bar_rdone.  cos_ij is recovered from
+          // An A tile is [128 rows][64 classes] (128 B rows, 16 B chunks XOR-swizzled with row & 7).  Warp ew owns the
+          // 8 classes of chunk ew, lane L the rows L, L+32, L+64, L+96: 4 conflict-free 16 B loads per k-block, taken
+          // once the tile's MMAs have retired (bar_empty) and released to the producer at once (bar_rdone); the row
+          // sums are then reduced with shuffles -- no shared-memory traffic, no CTA barrier.  cos_ij is recovered from
           // the stash: E' = exp2(s2 cos - ref2)  =>  cos = log2(E') / s2 + ref2 / s2  (E' = 0: target / clamped / pad).
           const int ew = warp - EPI_WARP0;
-          if (threadIdx.x - EPI_WARP0 * 32 < 128) side_rho[threadIdx.x - EPI_WARP0 * 32] = a.rho[w.m0 + (threadIdx.x - EPI_WARP0 * 32)];
-          epi_bar_sync();
+          float rh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rh[j] = a.rho[w.m0 + lane + 32 * j];
           for (int kb = w.kb0; kb < w.kb1; ++kb) {
             mbar_wait(bar_empty + 8 * side_stage, side_phase);
             const uint32_t sa = tiles_base + side_stage * STAGE_BYTES;
-            float a0 = 0.f, a1 = 0.f;
+            uint4 q4[4];
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-              const int ar = ew * 16 + rr;
-              uint32_t word;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word)
-                           : "r"(sa + ar * 128 + ((((lane >> 2) ^ (ar & 7)) << 4) | ((lane & 3) << 2))));
-              const float v0 = __uint_as_float(word << 16), v1 = __uint_as_float(word & 0xffff0000u);
-              const float rh = side_rho[ar];
-              const float c0 = fmaf(fmaxf(__log2f(v0), -200.f), a.side_inv_s2, a.side_kappa);
-              const float c1 = fmaf(fmaxf(__log2f(v1), -200.f), a.side_inv_s2, a.side_kappa);
-              a0 = fmaf(rh * v0, c0, a0);
-              a1 = fmaf(rh * v1, c1, a1);
+            for (int j = 0; j < 4; ++j) {
+              const int ar = lane + 32 * j;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(q4[j].x), "=r"(q4[j].y), "=r"(q4[j].z), "=r"(q4[j].w)
+                           : "r"(sa + ar * 128 + ((ew ^ (ar & 7)) << 4)));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_local(bar_rdone + 8 * side_stage);
-            float* red = side_red + (kb & 1) * NUM_EPI_WARPS * 64;
-            reinterpret_cast<float2*>(red + ew * 64)[lane] = make_float2(a0, a1);
-            epi_bar_sync();
-            if (ew < 2) {
-              float t = 0.f;
-#pragma unroll
-              for (int k = 0; k < NUM_EPI_WARPS; ++k) t += red[k * 64 + ew * 32 + lane];
-              atomicAdd(a.rsum + (int64_t)kb * BK + ew * 32 + lane, t);
+            if (a.side_debug == 1) {
+              if ((q4[0].x ^ q4[1].x ^ q4[2].x ^ q4[3].x) == 0x12345678u) atomicAdd(a.rsum, 1.f);
+              if (++side_stage == STAGES) { side_stage = 0; side_phase ^= 1; }
+              continue;
             }
+            float acc8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc8[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t ww[4] = {q4[j].x, q4[j].y, q4[j].z, q4[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float v0 = __uint_as_float(ww[e] << 16), v1 = __uint_as_float(ww[e] & 0xffff0000u);
+                const float c0 = fmaf(fmaxf(lg2(v0), -200.f), a.side_inv_s2, a.side_kappa);
+                const float c1 = fmaf(fmaxf(lg2(v1), -200.f), a.side_inv_s2, a.side_kappa);
+                acc8[2 * e] = fmaf(rh[j] * v0, c0, acc8[2 * e]);
+                acc8[2 * e + 1] = fmaf(rh[j] * v1, c1, acc8[2 * e + 1]);
+              }
+            }
+            // transposed butterfly over the 32 lanes: 8 -> 4 -> 2 -> 1 values per lane, then two plain steps
+#pragma unroll
+            for (int sft = 4; sft >= 1; sft >>= 1) {
+              const bool upper = (lane & sft) != 0;
+#pragma unroll
+              for (int e = 0; e < sft; ++e) {
+                const float send = upper ? acc8[e] : acc8[e + sft];
+                const float keep = upper ? acc8[e + sft] : acc8[e];
+                acc8[e] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+              }
+            }
+            float t = acc8[0];
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 16);
+            // lane L (< 8) now holds class bit-reversal-free index: value e = (L&4 ? 4:0)|(L&2 ? 2:0)|(L&1 ? 1:0)
+            if (lane < 8) atomicAdd(a.rsum + (int64_t)kb * BK + ew * 8 + lane, t);
             if (++side_stage == STAGES) { side_stage = 0; side_phase ^= 1; }
           }
         }
@@ -890,6 +930,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }, release);
       }
     }
+    if (AS && res_m >= 0) flush_stats();
   }
   __syncwarp();
   tc_fence_before();
@@ -981,14 +1022,18 @@ int variant_of(const MhParams& p) {
 
 template <int MODE>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
-  switch (variant_of(args.p)) {
+  const int v = variant_of(args.p);
+  if (MODE == MODE_FWDS && v != V_PLAIN && v != V_CLAMP) {
+    mh_set_error("the forward stash is only built for the plain / clamp families (see mh_tc_stash_ok)");
+    return MH_ERR_ARG;
+  }
+  constexpr int M2 = MODE == MODE_FWDS ? MODE_FWD : MODE;       // never instantiated for FWDS (guarded above)
+  switch (v) {
     case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, st);
     case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, st);
-    case V_SPHERE:
-      if (MODE == MODE_FWDS) { mh_set_error("the forward stash is not available for SphereFace"); return MH_ERR_ARG; }
-      return launch<MODE == MODE_FWDS ? MODE_FWD : MODE, V_SPHERE>(ta, tb, args, st);
-    case V_MV: return launch<MODE, V_MV>(ta, tb, args, st);
-    default: return launch<MODE, V_CURR>(ta, tb, args, st);
+    case V_SPHERE: return launch<M2, V_SPHERE>(ta, tb, args, st);
+    case V_MV: return launch<M2, V_MV>(ta, tb, args, st);
+    default: return launch<M2, V_CURR>(ta, tb, args, st);
   }
 }
 
@@ -1011,8 +1056,16 @@ int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
 
 }  // namespace
 
-// two statistics records per 256-wide class tile (one per 128-column epilogue half)
-extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { return 2 * ((C_pad + BN - 1) / BN); }
+// One statistics record per CTA pair and 128-column epilogue half: a pair accumulates its rows' statistics in registers
+// over all the class tiles it sweeps.  (The argument is kept for ABI stability; the count no longer depends on C.)
+extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { (void)C_pad; return 2 * (int64_t)(num_sms() / 2); }
+
+// records of rows a pair never visits stay at the merge identity (max = -inf, sums = 0)
+__global__ void stats_identity_kernel(float* __restrict__ st, int64_t n_parts, int64_t B_pad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = n_parts * MH_ST_PLANES * B_pad;
+  if (i < n) st[i] = ((i / B_pad) % MH_ST_PLANES == MH_ST_M) ? -INFINITY : 0.f;
+}
 
 // Fixed-reference softmax (and with it the forward stash) is used when every possible non-target term
 // exp2(z log2e - ref), ref = s log2e umax - 102, is a normal fp32 AND bf16 number with head-room for the row sums and
@@ -1061,6 +1114,10 @@ static int launch_s_tiles(const mh_config* cfg_host, const void* x_hat_bf16, int
   CUtensorMap tb;
   if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN / 2)) return e;
   const int64_t rows_per_launch = (int64_t)units * BMT;
+  if (stats_tiles) {
+    const int64_t n = 2 * (int64_t)units * MH_ST_PLANES * B_pad;
+    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * units, B_pad);
+  }
   for (int64_t r0 = 0; r0 < B_pad; r0 += rows_per_launch) {
     const int64_t rows = std::min(rows_per_launch, B_pad - r0);
     if (r0 >= B) break;                                               // only padding rows left
@@ -1136,6 +1193,7 @@ static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad,
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
   a.rho = rho; a.side_kappa = kappa; a.side_inv_s2 = inv_s2; a.rsum = r_colsum;
+  { const char* e = getenv("MH_DX_SIDE_DEBUG"); a.side_debug = e ? atoi(e) : 0; }
   if (rho) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
   return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }

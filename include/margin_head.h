@@ -142,7 +142,8 @@ int mh_row_params(const mh_config* cfg_host, int64_t B, const float* xnorm, cons
 
 /* ---- tensor-core path (bf16 operands, fp32 accumulate, tcgen05 + TMEM + TMA) ------------------ */
 
-/* Number of statistics records the forward writes per row, = 2 * ceil(C_pad / MH_NTILE_FWD). */
+/* Number of statistics records the forward keeps per row: one per CTA pair and 128-column epilogue half
+ * (2 * (#SMs / 2) = 148 on a B200; independent of C_pad, which is accepted for ABI stability). */
 int64_t mh_fwd_num_tiles(int64_t C_pad);
 
 /* Host-only test hook: the static tile schedule of the A-stationary forward / backward-G kernels for `units` CTA

@@ -9,19 +9,16 @@ import json
 import subprocess
 import sys
 
-NAMES = {
-    "tc_kernel<(int)0": "mh_tc_forward", "tc_kernel<(int)1": "mh_tc_backward_g", "tc_kernel<(int)2": "mh_tc_backward_dx",
-    "tc_kernel<(int)3": "mh_tc_backward_dw", "tc_kernel<(int)4": "mh_tc_backward_dw_fused",
-    "prologue_w": "mh_prologue_w", "norm_backward_w": "mh_norm_backward_w",
-}
+NAMES = {"prologue_w": "mh_prologue_w", "norm_backward_w": "mh_norm_backward_w"}
+# tc_kernel<MODE, VARIANT>: MODE 0 FWD, 1 FWDS (forward + stash), 2 BWD_G, 3 DX, 4 DW (see tc_head.cu)
+TC_MODES = ["mh_tc_forward", "mh_tc_forward_stash", "mh_tc_backward_g", "mh_tc_backward_dx", "mh_tc_backward_dw_fused"]
 
 
 def api_name(kernel):
     import re
     m = re.search(r"tc_kernel<\(?(?:int\))?(\d)", kernel)
     if m:
-        return ["mh_tc_forward", "mh_tc_backward_g", "mh_tc_backward_dx", "mh_tc_backward_dw",
-                "mh_tc_backward_dw_fused"][int(m.group(1))]
+        return TC_MODES[int(m.group(1))]
     for k, v in NAMES.items():
         if k in kernel:
             return v

@@ -1,0 +1,41 @@
+"""Per-kernel CUDA-event timings of one fused ArcFace step at the bench shape (B=1024, C=2M), a few repetitions."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import face_recognition_models_b200 as pkg
+from face_recognition_models_b200 import _lib as L
+B, Cn = 1024, int(os.environ.get("C", 2_000_000))
+head = pkg.ArcFace(512, Cn, s=64.0, m=0.5, easy_margin=False).cuda()
+g = torch.Generator(device="cuda").manual_seed(4)
+with torch.no_grad():
+    head.weight.normal_(0, 0.01, generator=g)
+x = torch.randn(B, 512, device="cuda", generator=g)
+y = torch.randint(0, Cn, (B,), device="cuda", generator=g)
+def step():
+    xg = x.detach().requires_grad_(True); head.weight.grad = None
+    out = head.fused_loss(xg, y); out.loss.backward(); return out
+def measure(tag):
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+    L.PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): step()
+    e1.record(); torch.cuda.synchronize()
+    prof, L.PROFILE = L.PROFILE, None
+    agg = {}
+    for name, a, b, n in prof:
+        if n: agg.setdefault(name, []).append(a.elapsed_time(b))
+    print(f"{tag:28s} step_ms %.3f" % (e0.elapsed_time(e1) / 20), " ".join(f"{k[3:]}={sum(v)/len(v):.3f}" for k, v in agg.items() if sum(v)/len(v) > 0.05), flush=True)
+
+# settings: "ENV=VAL,ENV=VAL;..." (MH_BACKWARD sets head.backward_mode); each measured twice, interleaved
+settings = [dict(kv.split("=") for kv in grp.split(",") if kv) for grp in os.environ.get("SETTINGS", "").split(";")]
+for rep in range(2):
+    for st in settings:
+        for k in ("MH_DX_SIDE_DEBUG", "MH_EXP"):
+            os.environ.pop(k, None)
+        head.backward_mode = "auto"
+        for k, v in st.items():
+            if k == "MH_BACKWARD": head.backward_mode = v
+            else: os.environ[k] = v
+        measure(",".join(f"{k}={v}" for k, v in st.items()) or "default")

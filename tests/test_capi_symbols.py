@@ -56,7 +56,7 @@ def test_argument_validation_without_gpu(lib):
     assert st == -1 and b"null pointer" in lib.mh_last_error()
     st = lib.mh_tc_backward_dw(ctypes.c_void_p(16), 100, 256, ctypes.c_void_p(16), ctypes.c_void_p(16), None)
     assert st == -1 and b"padded" in lib.mh_last_error()
-    assert lib.mh_fwd_num_tiles(2000128) == 2 * 7813
+    assert lib.mh_fwd_num_tiles(2000128) == 148              # one record per CTA pair and column half (148 SMs)
 
 
 def test_no_cpu_fallback():

@@ -4,7 +4,9 @@
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPUs
 
 A step = one pass of the hot path over one batch: prologues (normalise W and x), fused forward
-(cos-GEMM + margin + online softmax-CE + top-1/5), backward (G recompute, dx, dW, normalise-backward).
+(cos-GEMM + margin + softmax-CE + top-1/5), backward (dx, dW, normalise-backward).  The headline runs the default
+backward mode of the head ("stash": the training forward also writes bf16 exp2(z - ref), the backward is two GEMMs);
+`alt_backward` times the "recompute" mode (nothing B x C written by the forward, logit tiles recomputed) the same way.
 Workload (BASELINE configs[3]): ArcFace(s=64, m=0.5, easy_margin=False), d=512, C=2,000,000 synthetic
 identities, B=1024 per GPU; with N>1 the class dimension is sharded over the N ranks (weak scaling:
 per-GPU tensor work 6*B*C*d is constant) with NCCL all-gather / all-reduce / reduce-scatter.
@@ -44,19 +46,34 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe), through NVML every
+    ~10 ms (the timed regions are short); falls back to an `nvidia-smi -lms 50` pipe when NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, power_w, set(reasons))
         self.proc = None
         self.active = False
+        self._stop = False
         self._t = None
+        self._nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nvml = pynvml
+            self._t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self._t.start()
+            return
+        except Exception:  # noqa: BLE001
+            self._nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
@@ -66,12 +83,41 @@ class ClockSampler:
         self._t = threading.Thread(target=self._pump, daemon=True)
         self._t.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
+    def _poll_nvml(self):
+        n = self._nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            mx = 0.0
+        while not self._stop:
             if self.active:
-                self.rows.append(line.strip())
+                try:
+                    sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    pw = n.nvmlDeviceGetPowerUsage(self._h) / 1e3
+                    self.samples.append((sm, mx, pw, {k for k, b in bits.items() if mask & b}))
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.01)
+
+    def _pump(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            if not self.active:
+                continue
+            f = [x.strip() for x in line.strip().split(",")]
+            try:
+                self.samples.append((float(f[1]), float(f[2]), float(f[3]),
+                                     {n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")}))
+            except (ValueError, IndexError):
+                continue
 
     def stop(self):
+        self._stop = True
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -80,23 +126,14 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = set()
+        for s_ in self.samples:
+            reasons |= s_[3]
+        return {"sm_mhz": statistics.median(s_[0] for s_ in self.samples), "sm_max_mhz": max(s_[1] for s_ in self.samples),
+                "power_w_max": round(max(s_[2] for s_ in self.samples), 1), "reasons": sorted(reasons),
+                "samples": len(self.samples), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -147,7 +184,9 @@ def run_reference(args):
     if rank != 0:
         return
     B = 32 if host_ram_gb() > 24 else 8
-    r = cpu_reference_run(args.steps, min(args.warmup, 1), B)
+    # bounded sample: ~0.3 s per step at C_SAMPLE on 16 cores; shrink the class slice when many steps are requested
+    Cn = C_SAMPLE if args.steps <= 30 else max(C_TOTAL // 64, C_TOTAL // (8 * -(-args.steps // 30)))
+    r = cpu_reference_run(args.steps, min(args.warmup, 1), B, Cn)
     line = {
         "impl": "reference", "metric": "margin-head fwd+bwd samples/s at C=2M", "value": r["value"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
@@ -177,6 +216,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"                # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     Cn, B = args.C, args.B
     peaks = load_peaks()
@@ -250,6 +291,18 @@ def run_b200(args):
     L.PROFILE = []
     ms_total = timed(step_resident, args.steps)
     prof, L.PROFILE = L.PROFILE, None
+    # ---- the other backward mode (recompute: north_star's "backward recomputes logit tiles"), same protocol ---------
+    alt = None
+    if eng.stash_ok():
+        eng.backward_mode = "recompute"
+        for _ in range(3):
+            step_resident()
+        ms_alt = timed(step_resident, args.steps)
+        eng.backward_mode = "auto"
+        alt = {"backward": "recompute (forward writes nothing of size B x C; backward recomputes the logit tiles, 4 GEMM passes)",
+               "value": B * world * args.steps / (ms_alt * 1e-3), "unit": "samples/s", "ms_per_step": ms_alt / args.steps}
+        for _ in range(2):
+            step_resident()
     # ---- end-to-end arm (host buffers) ------------------------------------------------------------------
     x_dev, y_dev = torch.empty_like(x), torch.empty_like(y)
     for _ in range(2):
@@ -273,7 +326,7 @@ def run_b200(args):
     algo = {
         "mh_tc_forward": ("tensor", gemm_flops), "mh_tc_backward_g": ("tensor", gemm_flops),
         "mh_tc_backward_dx": ("tensor", gemm_flops), "mh_tc_backward_dw": ("tensor", gemm_flops),
-        "mh_tc_backward_dw_fused": ("tensor", gemm_flops),
+        "mh_tc_backward_dw_fused": ("tensor", gemm_flops), "mh_tc_backward_dx_stash": ("tensor", gemm_flops),
         "mh_prologue_w": ("hbm", 6.0 * C_loc * D + 4.0 * C_loc),
         "mh_norm_backward_w": ("hbm", (4.0 + 2.0 + 4.0) * C_loc * D),
     }
@@ -293,7 +346,7 @@ def run_b200(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom)
+        traffic = json.load(open(tp)).get(dom.replace("_stash", ""))
     roofline = {
         "kernel": dom, "bound": "tensor", "achieved": kernels[dom]["achieved"], "peak": peaks["tflops_sustained"],
         "unit": "TFLOP/s", "frac": round(kernels[dom]["achieved"] / peaks["tflops_sustained"], 4), "traffic": traffic,
@@ -329,7 +382,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8) * world, "d2h_bytes_per_step": 12 * world},
             "gpu_launches": n_launch,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "alt_backward": alt,
             "clocks": sampler.summary() if sampler else None,
         }
         print(json.dumps(line), flush=True)
@@ -340,8 +393,8 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--C", type=int, default=C_TOTAL)
     ap.add_argument("--B", type=int, default=B_PER_GPU)

@@ -35,7 +35,6 @@ constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int STG_WARP_BYTES = 32 * 128;          // output staging per epilogue warp: 32 rows x 128 B, XOR-swizzled
-constexpr int DX_SIDE_BYTES = 0;
 
 enum { MODE_FWD = 0, MODE_FWDS = 1, MODE_BWD_G = 2, MODE_DX = 3, MODE_DW = 4 };
 // A-stationary (FWD / FWDS / BWD_G): the pair's x^ tile (128 rows x 512 per CTA = 128 KB) stays resident in shared
@@ -47,17 +46,20 @@ constexpr int A_RESIDENT_BYTES = BM * MH_D * 2;                                 
 constexpr int mode_bn(int mode) { return mode == MODE_DX ? 512 : 256; }          // accumulator columns per tile
 constexpr int mode_nbuf(int mode) { return mode_bn(mode) == 512 ? 1 : 2; }        // TMEM accumulators in flight
 constexpr int mode_stage_bytes(int mode) { return (mode_astat(mode) ? 0 : A_STAGE_BYTES) + (mode_bn(mode) / 2) * BK * 2; }
-constexpr int mode_stages(int mode) { return (mode == MODE_FWD || mode == MODE_DW) ? 6 : 4; }
+constexpr int mode_stages(int mode) { return mode == MODE_FWD ? 6 : 4; }
+// DW: the epilogue's w^ tile (128 classes x 256 d, bf16) is TMA-loaded into shared memory once per tile
+constexpr int W_TILE_BYTES = BM * BN * 2;                                         // 64 KB
 constexpr int mode_smem_bytes(int mode) {
   return (mode_astat(mode) ? A_RESIDENT_BYTES : 0) + mode_stages(mode) * mode_stage_bytes(mode) + 1024 /*align slack*/ +
          256 /*barriers*/ + (mode_staged(mode) ? NUM_EPI_WARPS * STG_WARP_BYTES : 0) +
-         (mode == MODE_DX ? DX_SIDE_BYTES : 0);
+         (mode == MODE_DW ? W_TILE_BYTES : 0);
 }
 static_assert(mode_smem_bytes(MODE_FWD) <= 232448 && mode_smem_bytes(MODE_FWDS) <= 232448 &&
               mode_smem_bytes(MODE_BWD_G) <= 232448 && mode_smem_bytes(MODE_DX) <= 232448 &&
               mode_smem_bytes(MODE_DW) <= 232448, "smem budget");
 
 struct TcArgs {
+  CUtensorMap tmW;             // DW fused: w^ [C_pad, 512], box [64 d][128 classes] (epilogue operand)
   int m_tiles, n_tiles, n_split, k_blocks_total, k_blocks_per_split;
   int64_t total_tiles;
   int sG, sE, n_fixed;         // A-stationary schedule (see StatIter)
@@ -118,6 +120,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// TMA load into this CTA's shared memory, completing on this CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_local(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -564,7 +573,8 @@ __device__ __forceinline__ void chunk_loop(uint32_t taddr, Body&& body, Loaded&&
 
 template <int MODE, int V>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ TcArgs a) {
   constexpr int STAGES = mode_stages(MODE);
   constexpr int STAGE_BYTES = mode_stage_bytes(MODE);
   constexpr bool AS = mode_astat(MODE);              // x^ tile resident in smem, only w^ streams
@@ -584,8 +594,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t ares_base = smem_base;                             // AS: resident A, 8 k-blocks x 16 KB
   const uint32_t tiles_base = smem_base + (AS ? A_RESIDENT_BYTES : 0);
   uint8_t* tiles_ptr = smem_raw + (tiles_base - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + STAGES * STAGE_BYTES);
-  uint8_t* stg_all = tiles_ptr + STAGES * STAGE_BYTES + 256;        // output staging (FWDS / BWD_G / DW)
+  constexpr int W_BYTES = (MODE == MODE_DW) ? W_TILE_BYTES : 0;
+  const uint32_t wtile_base = tiles_base + STAGES * STAGE_BYTES;    // DW: w^ tile, 4 boxes [128 classes][64 d] (1024 B aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + STAGES * STAGE_BYTES + W_BYTES);
+  uint8_t* stg_all = tiles_ptr + STAGES * STAGE_BYTES + W_BYTES + 256;   // output staging (FWDS / BWD_G / DW)
   const uint32_t bar_full = smem_u32(bars);                         // [STAGES]
   const uint32_t bar_empty = bar_full + 8 * MAX_STAGES;             // [STAGES]
   const uint32_t bar_tfull = bar_empty + 8 * MAX_STAGES;            // [2]
@@ -594,12 +606,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t bar_afull = bar_full + 8 * (2 * MAX_STAGES + 5);   // AS: resident A landed
   const uint32_t bar_afree = bar_afull + 8;                         // AS: every MMA that read the resident A retired
   const uint32_t bar_rdone = bar_afree + 8;                         // DX side pass: [STAGES] the epilogue warps read the A tile
+  const uint32_t bar_wfull = bar_rdone + 8 * MAX_STAGES;            // DW: w^ tile landed
+  const uint32_t bar_wempty = bar_wfull + 8;                        // DW: the epilogue warps are done with the w^ tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (MODE == MODE_DW) prefetch_tmap(&a.tmW);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 2);                   // leader's expect_tx arrive + the peer producer's arrive
       mbar_init(bar_empty + 8 * s, 1);
@@ -611,6 +626,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     mbar_init(bar_afull, 2);
     mbar_init(bar_afree, 1);
     for (int s = 0; s < STAGES; ++s) mbar_init(bar_rdone + 8 * s, NUM_EPI_WARPS);
+    mbar_init(bar_wfull, 1);
+    mbar_init(bar_wempty, NUM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
@@ -665,6 +682,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 tma_load_2d_2sm(sb + (nh * (GW / 64) + bx) * 8192, &tmB, fb, w.n0 + nh * BN + rank * GW + 64 * bx, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (MODE == MODE_DW && !a.raw_dw) {
+          // w^ tile for this tile's epilogue.  Issued after the k-loop loads so that waiting for the previous tile's
+          // epilogue (which overlaps this tile's MMAs) never holds back the operand pipeline.
+          if (tile_j > 1) mbar_wait(bar_wempty, (tile_j - 2) & 1);
+          mbar_expect_tx(bar_wfull, W_TILE_BYTES);
+#pragma unroll
+          for (int bx = 0; bx < BN / 64; ++bx)
+            tma_load_2d_local(wtile_base + bx * (BM * 128), &a.tmW, bar_wfull, w.n0 + 64 * bx, w.m0);
         }
       }
     }
@@ -887,21 +913,27 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         float rj = 0.f, coef = 1.f;
         if (!raw && row < a.C) { rj = a.rsum[row]; coef = a.gscal[0] * a.inv_norm[row]; }
         if (!raw && row >= a.C) coef = 0.f;
-        const __nv_bfloat16* wrow = a.w_hat + row * MH_D + w.n0 + cbase;          // rows >= C of w_hat are zero
         const int rows_ok = raw ? 32 : (int)max((int64_t)0, min((int64_t)32, a.C - ((int64_t)w.m0 + q * 32)));
         const int64_t opitch = raw ? (int64_t)MH_D : a.ld;
         mbar_wait(bar_tfull + 8 * buf, bphase);
         tc_fence_after();
+        if (!raw) mbar_wait(bar_wfull, it & 1);            // this tile's w^ [128 classes][256 d] is in shared memory
         chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
           float o[32];
           if (raw) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(cur[k]);
           } else {
-            const uint4* wsrc = reinterpret_cast<const uint4*>(wrow + c * 32);
+            // w^ row r, d columns cbase + 32c ..: box (cbase + 32c) / 64, 16 B chunks XOR-swizzled with r & 7
+            const int dcol = cbase + c * 32;
+            const uint32_t wrow_s = wtile_base + (dcol >> 6) * (BM * 128) + r * 128;
+            const int ci0 = (dcol & 63) >> 3;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-              const uint4 wq = __ldg(wsrc + k4);
+              uint4 wq;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w)
+                           : "r"(wrow_s + (((ci0 + k4) ^ (r & 7)) << 4)));
               const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -910,6 +942,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 o[k] = (__uint_as_float(cur[k]) - wf.x * rj) * coef;
                 o[k + 1] = (__uint_as_float(cur[k + 1]) - wf.y * rj) * coef;
               }
+            }
+            if (c == NCHUNK - 1) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive_local(bar_wempty);      // producer may fetch the next tile's w^
             }
           }
           if (raw || a.layout == MH_LAYOUT_CD) {
@@ -1250,5 +1286,6 @@ extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_
   a.out = dW; a.raw_dw = 0; a.layout = layout; a.ld = ld;
   a.w_hat = (const __nv_bfloat16*)w_hat_bf16; a.inv_norm = inv_norm; a.gscal = gscal;
   a.rsum = const_cast<float*>(r_colsum);
+  if (int e = make_tmap(&a.tmW, w_hat_bf16, C_pad, MH_D, BM)) return e;       // epilogue operand: boxes [64 d][128 classes]
   return launch_dw(G_bf16, B_pad, C, C_pad, x_hat_bf16, a, (cudaStream_t)stream);
 }

@@ -11,7 +11,7 @@ import sys
 
 NAMES = {"prologue_w": "mh_prologue_w", "norm_backward_w": "mh_norm_backward_w"}
 # tc_kernel<MODE, VARIANT>: MODE 0 FWD, 1 FWDS (forward + stash), 2 BWD_G, 3 DX, 4 DW (see tc_head.cu)
-TC_MODES = ["mh_tc_forward", "mh_tc_forward_stash", "mh_tc_backward_g", "mh_tc_backward_dx", "mh_tc_backward_dw_fused"]
+TC_MODES = ["mh_tc_forward", "mh_tc_forward", "mh_tc_backward_g", "mh_tc_backward_dx", "mh_tc_backward_dw_fused"]
 
 
 def api_name(kernel):

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mh_pair_cosine": [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp],
     "mh_tc_fixref_ok": [_cfgp, _i64],
     "mh_tc_stash_ok": [_cfgp, _i64],
     "mh_stash_prep": [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],

@@ -281,6 +281,14 @@ int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, const float*
 /* gscal[0] = upstream_grad(loss_id) / B_total, gscal[1] = upstream_grad(loss_g): device floats so
  * that a GradScaler-scaled backward (model_utils.py:185) needs no host sync. */
 
+/* ---- pair verification (the device-side piece of the LFW evaluator) ------------------- */
+
+/* cos_out[i] = <e1_i, e2_i> / (max(|e1_i|,1e-12) * max(|e2_i|,1e-12)) for N embedding pairs of dimension d
+ * (row pitches ld1, ld2 in elements; dtype MH_F32 / MH_BF16 / MH_F16): F.normalize on both backbone outputs and the
+ * row-wise dot of model_utils.py:333-335, 367-369, 392-394.  HBM-bound, one warp per pair. */
+int mh_pair_cosine(const void* e1, const void* e2, int dtype, int64_t N, int64_t d, int64_t ld1, int64_t ld2,
+                   float* cos_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,8 +18,15 @@ with torch.no_grad():
     head.weight.normal_(0, 0.01)
 x = torch.randn(a.B, 512, device="cuda", requires_grad=True)
 y = torch.randint(0, a.C, (a.B,), device="cuda")
+def zero():                         # optimizer.zero_grad(set_to_none=True): no gradient-accumulation kernels
+    x.grad = None
+    head.weight.grad = None
+
+
 for _ in range(a.warmup):
+    zero()
     head.fused_loss(x, y).loss.backward()
+zero()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 out = head.fused_loss(x, y)

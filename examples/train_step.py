@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--classes", type=int, default=10575)
     ap.add_argument("--backbone", default="resnet50")
     ap.add_argument("--lambda_g", type=float, default=0.0)
+    ap.add_argument("--lfw_pairs", type=int, default=6000, help="synthetic verification pairs (0 = skip)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -69,6 +70,14 @@ def main():
         if rank == 0:
             print(f"step {step}: loss {lv:.4f} acc@1 {float(out.acc1):.2f} acc@5 {float(out.acc5):.2f} "
                   f"({a.batch * world / (time.time() - t0):.1f} img/s)")
+    if rank == 0 and a.lfw_pairs > 0:
+        # LFW-style 10-fold verification (model_utils.py:416-474) on synthetic embedding pairs: the per-pair cosine runs
+        # on the GPU (mh_pair_cosine), the fold statistics are the reference's scikit-learn calls
+        from oracle.verification_oracle import synthetic_pairs
+        e1, e2, same = synthetic_pairs(a.lfw_pairs, 512, 1.5, seed=5)
+        acc, acc_std, auc, auc_std = pkg.verification.cross_validate_kfold(
+            torch.from_numpy(e1).to(dev), torch.from_numpy(e2).to(dev), torch.from_numpy(same), k_fold=10)
+        print(f"LFW-protocol 10-fold on {a.lfw_pairs} synthetic pairs: accuracy {acc:.3f}% +- {acc_std:.3f}, AUC {auc:.4f} +- {auc_std:.4f}")
     if world > 1:
         dist.destroy_process_group()
 

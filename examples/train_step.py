@@ -73,10 +73,17 @@ def main():
     if rank == 0 and a.lfw_pairs > 0:
         # LFW-style 10-fold verification (model_utils.py:416-474) on synthetic embedding pairs: the per-pair cosine runs
         # on the GPU (mh_pair_cosine), the fold statistics are the reference's scikit-learn calls
-        from oracle.verification_oracle import synthetic_pairs
-        e1, e2, same = synthetic_pairs(a.lfw_pairs, 512, 1.5, seed=5)
-        acc, acc_std, auc, auc_std = pkg.verification.cross_validate_kfold(
-            torch.from_numpy(e1).to(dev), torch.from_numpy(e2).to(dev), torch.from_numpy(same), k_fold=10)
+        g = torch.Generator(device=dev).manual_seed(5)
+        half = a.lfw_pairs // 2
+
+        def unit(n):
+            return torch.nn.functional.normalize(torch.randn(n, 512, device=dev, generator=g), dim=1)
+
+        centre = unit(half)                                       # same-identity pairs share a centre
+        e1 = torch.cat([centre + 1.5 * unit(half), unit(half) + 1.5 * unit(half)])
+        e2 = torch.cat([centre + 1.5 * unit(half), unit(half) + 1.5 * unit(half)])
+        same = torch.cat([torch.ones(half, dtype=torch.long), torch.zeros(half, dtype=torch.long)])
+        acc, acc_std, auc, auc_std = pkg.verification.cross_validate_kfold(e1, e2, same, k_fold=10)
         print(f"LFW-protocol 10-fold on {a.lfw_pairs} synthetic pairs: accuracy {acc:.3f}% +- {acc_std:.3f}, AUC {auc:.4f} +- {auc_std:.4f}")
     if world > 1:
         dist.destroy_process_group()

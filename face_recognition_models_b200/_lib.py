@@ -29,7 +29,7 @@ class MhConfig(C.Structure):
 
 # enums of include/margin_head.h
 FAMILY = dict(arcface=0, cosface=1, sphereface=2, mv_am=3, mv_arc=4, curricularface=5, adaface=6,
-              elastic_cos=7, elastic_arc=8, magface=9)
+              elastic_cos=7, elastic_arc=8, magface=9, vpl_arcface=10)
 LAYOUT_CD, LAYOUT_DC = 0, 1
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 RP = dict(SCALE=0, THR=1, ZT=2, DZT=3, T=4, DZT_DN=5, DLG_DN=6, NORMS=7)
@@ -56,6 +56,7 @@ SIGNATURES = {
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mh_vpl_mix": [_vp, _vp, _vp, C.c_float, _i64, _i64, _vp, _vp, _vp],
     "mh_pair_cosine": [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp],
     "mh_tc_fixref_ok": [_cfgp, _i64],
     "mh_tc_stash_ok": [_cfgp, _i64],

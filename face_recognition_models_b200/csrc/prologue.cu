@@ -133,6 +133,59 @@ extern "C" int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// vpl_mix: v_j = (1 - a_j) w^_j + a_j m^_j, a_j = lamda * 1[life_j > 0]  (VPLArcFace, criterion.py:716-724).
+// One warp per class: reads w^_j (bf16, 1 KB) and mem_j (fp32, 2 KB), writes v_j (bf16, 1 KB).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vpl_mix_kernel(const __nv_bfloat16* __restrict__ what, const float* __restrict__ mem,
+                                                      const float* __restrict__ life, float lamda, int64_t C, int64_t C_pad,
+                                                      __nv_bfloat16* __restrict__ v, float* __restrict__ alpha) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= C_pad) return;
+  uint2* dst = reinterpret_cast<uint2*>(v + row * MH_D);
+  if (row >= C) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = make_uint2(0u, 0u);
+    return;
+  }
+  const float al = (life[row] > 0.f) ? lamda : 0.f;        // fl32(mask * lamda), as the reference's float32 mask
+  const float be = 1.f - al;
+  if (lane == 0) alpha[row] = al;
+  float4 m4[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    m4[k] = (al != 0.f) ? __ldg(reinterpret_cast<const float4*>(mem + row * MH_D) + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += m4[k].x * m4[k].x + m4[k].y * m4[k].y + m4[k].z * m4[k].z + m4[k].w * m4[k].w;
+  }
+  ss = warp_sum(ss);
+  const float am = al / fmaxf(sqrtf(ss), 1e-12f);          // a_j / |mem_j|  (F.normalize, criterion.py:720)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint2 wq = reinterpret_cast<const uint2*>(what + row * MH_D)[lane + 32 * k];
+    const float2 w0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wq.x));
+    const float2 w1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wq.y));
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(be, w0.x, am * m4[k].x), fmaf(be, w0.y, am * m4[k].y));
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(be, w1.x, am * m4[k].z), fmaf(be, w1.y, am * m4[k].w));
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    dst[lane + 32 * k] = pk;
+  }
+}
+
+extern "C" int mh_vpl_mix(const void* w_hat_bf16, const float* mem, const float* life, float lamda, int64_t C, int64_t C_pad,
+                          void* v_bf16, float* alpha_out, void* stream) {
+  MH_CHECK_ARG(w_hat_bf16 && mem && life && v_bf16 && alpha_out, "null pointer");
+  MH_CHECK_ARG(C > 0 && C_pad >= C, "bad shape");
+  MH_CHECK_ARG(((uintptr_t)mem & 15) == 0 && ((uintptr_t)w_hat_bf16 & 7) == 0 && ((uintptr_t)v_bf16 & 7) == 0, "alignment");
+  vpl_mix_kernel<<<(unsigned)((C_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)w_hat_bf16, mem, life, lamda, C, C_pad, (__nv_bfloat16*)v_bf16, alpha_out);
+  MH_LAUNCH_OK();
+  return MH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // prologue_x: one warp per embedding row. Reads x once (4*512 B in fp32), gathers the target class
 // centre (4*512 B), writes x_hat bf16 (1 KB) + fp32 copy + three scalars.
 // ------------------------------------------------------------------------------------------------
@@ -392,6 +445,21 @@ __global__ void __launch_bounds__(1024) row_params_kernel(MhParams p, int64_t B,
         zt = p.s * cosf(th_m);
         dzt = p.s * sinf(th_m) / sqrtf(1.f - t * t) * in2 * inside;
       } break;
+      case MH_VPL_ARC: {                                  // criterion.py:724-749 (target column: cosine2 -> clamp -> margin)
+        // margins[i] = a_y = lamda * 1[life_y > 0]; target cosine = (1 - a_y) * <x^, w^_y> + a_y, both weights in fp32
+        const float al = margins[i], be = 1.f - al;
+        const float c2 = fmaf(be, tr, al);
+        const float tc = fminf(fmaxf(c2, p.lo), p.hi);
+        const float in2 = (c2 >= p.lo && c2 <= p.hi) ? 1.f : 0.f;
+        const float sin_t = sqrtf(1.f - tc * tc + 1e-9f);
+        const float phi = tc * p.cos_m - sin_t * p.sin_m;
+        const float dphi = p.cos_m + tc / sin_t * p.sin_m;
+        const bool take = p.easy_margin ? (tc > 0.f) : (tc > p.th);
+        const float alt = p.easy_margin ? tc : tc - p.mm;
+        zt = p.s * (take ? phi : alt);
+        dzt = p.s * (take ? dphi : 1.f) * in2 * be;       // d zt / d <x^, w^_y>
+        rowp[MH_RP_T * ldp + i] = tc;                     // pre-margin value at the target column (rank count)
+      } break;
       case MH_MAGFACE: {                                  // criterion.py:1244-1278
         float xc = fminf(fmaxf(xn, p.l_a), p.u_a);
         float in_n = (xn >= p.l_a && xn <= p.u_a) ? 1.f : 0.f;
@@ -417,7 +485,7 @@ __global__ void __launch_bounds__(1024) row_params_kernel(MhParams p, int64_t B,
     rowp[MH_RP_THR * ldp + i] = thr;
     rowp[MH_RP_ZT * ldp + i] = zt;
     rowp[MH_RP_DZT * ldp + i] = dzt;
-    rowp[MH_RP_T * ldp + i] = t;
+    if (p.family != MH_VPL_ARC) rowp[MH_RP_T * ldp + i] = t;
     rowp[MH_RP_DZT_DN * ldp + i] = dzt_dn;
     rowp[MH_RP_DLG_DN * ldp + i] = dlg_dn;
     rowp[MH_RP_NORMS * ldp + i] = norms;
@@ -435,8 +503,9 @@ extern "C" int mh_row_params(const mh_config* cfg_host, int64_t B, const float* 
   MH_CHECK_ARG(cfg_host && xnorm && t_raw && state && rowp, "null pointer");
   MH_CHECK_ARG(B > 0 && ldp >= B, "ldp must be >= B");
   MhParams p = mh_make_params(cfg_host);
-  MH_CHECK_ARG(p.family >= 0 && p.family <= MH_MAGFACE, "unknown family");
-  MH_CHECK_ARG((p.family != MH_ELASTIC_COS && p.family != MH_ELASTIC_ARC) || margins, "ElasticFace needs margins");
+  MH_CHECK_ARG(p.family >= 0 && p.family <= MH_VPL_ARC, "unknown family");
+  MH_CHECK_ARG((p.family != MH_ELASTIC_COS && p.family != MH_ELASTIC_ARC && p.family != MH_VPL_ARC) || margins,
+               "ElasticFace / VPL-ArcFace need the per-row margins / interpolation weights");
   MH_CHECK_ARG(p.family != MH_SPHEREFACE || (p.sphere_m >= 0 && p.sphere_m <= 5), "SphereFace m must be in 0..5");
   row_params_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p, B, xnorm, t_raw, margins, state, update_state, rowp, ldp);
   MH_LAUNCH_OK();

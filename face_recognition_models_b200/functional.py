@@ -79,6 +79,7 @@ class HeadEngine:
             setattr(self.cfg, k, v)
         self._ws: Dict[str, torch.Tensor] = {}
         self._gen = 0
+        self.vpl = None                 # VPLArcFace: dict(mem, life, lamda) set by the head before each forward
         # "auto" | "stash" | "recompute"; MH_BACKWARD in the environment overrides (A/B measurements)
         self.backward_mode = os.environ.get("MH_BACKWARD", "auto")
 
@@ -153,7 +154,22 @@ class HeadEngine:
             # every rank needs every row's target cosine (thresholds, EMA); only the owner computed it
             self.shard.comm.allreduce_sum_(t_raw)
 
-        if self.family in ("elastic_cos", "elastic_arc"):
+        w_gemm = w_hat
+        alpha = None
+        if self.family == "vpl_arcface":
+            # VPL-ArcFace (criterion.py:716-725): the GEMM runs against the mixed class vectors v_j; the per-row
+            # interpolation weight a_{y_i} enters the target logit through row_params' `margins` slot
+            if exact or self.shard.world > 1:
+                raise L.MarginHeadError("VPLArcFace runs on the single-GPU tensor-core path only")
+            alpha = self._buf("vpl_alpha", (Cn,), torch.float32, dev)
+            if self.vpl is not None:
+                w_gemm = self._buf("vpl_v", (C_pad, L.D), torch.bfloat16, dev)
+                L.call("mh_vpl_mix", _ptr(w_hat), _ptr(self.vpl["mem"]), _ptr(self.vpl["life"]), C.c_float(self.vpl["lamda"]),
+                       Cn, C_pad, _ptr(w_gemm), _ptr(alpha), st)
+            else:
+                alpha.zero_()
+            margins = alpha[labels].contiguous()
+        elif self.family in ("elastic_cos", "elastic_arc"):
             assert margins is not None and margins.numel() == B
             margins = margins.to(device=dev, dtype=torch.float32).contiguous()
             if self.cfg.plus:
@@ -185,7 +201,7 @@ class HeadEngine:
             scratch = self._buf("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev)
             if want_grad and self.stash_ok():
                 stash = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
-            L.call("mh_tc_forward", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_hat), Cn, C_pad, _ptr(rowp), B_pad,
+            L.call("mh_tc_forward", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_gemm), Cn, C_pad, _ptr(rowp), B_pad,
                    _ptr(label_local), _ptr(state), _ptr(stats_tiles), _ptr(stash), st)
             L.call("mh_merge_stats", _ptr(stats_tiles), n_tiles, B, B_pad, _ptr(scratch), _ptr(stats), st)
 
@@ -202,7 +218,7 @@ class HeadEngine:
         return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=w_hat, w_hat32=w_hat32, inv_norm=inv_norm,
                     x_hat=x_hat, x_hat32=x_hat32, xnorm=xnorm, label_local=label_local, rowp=rowp, rowout=rowout,
                     scalars=scalars, S=S, pre=pre, logits=logits, exact=exact, gen=self._gen, state=state,
-                    W_shape=tuple(W.shape), ld=ld, stash=stash)
+                    W_shape=tuple(W.shape), ld=ld, stash=stash, w_gemm=w_gemm, vpl_alpha=alpha)
 
     # -- backward of the fused loss ------------------------------------------------------------------
     def backward(self, ctx: Dict, g_loss: torch.Tensor, g_lossg: Optional[torch.Tensor],
@@ -227,6 +243,8 @@ class HeadEngine:
             return self._exact_grads(ctx, S, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]], need_dx, need_dw)
         w_hat, x_hat, label_local = ctx["w_hat"], ctx["x_hat"], ctx["label_local"]
         stash = ctx.get("stash")
+        if self.family == "vpl_arcface":
+            return self._backward_vpl(ctx, gscal, need_dx, need_dw)
         rsum = self._buf("r_colsum", (C_pad,), torch.float32, dev)
         ns = C.c_int(0)
         L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), st)
@@ -266,6 +284,43 @@ class HeadEngine:
             if stash is not None:
                 L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
                        _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
+        return dx, dW
+
+    def _backward_vpl(self, ctx, gscal, need_dx, need_dw):
+        """VPL-ArcFace backward on the stash: dx^ = diag(rho) E'.v + G_iy (1 - a_y) w^_y;  dw^_j = (1 - a_j) E'^T.(rho x^)
+        + the target term; the memory bank carries no gradient (oracle/vpl_oracle.py has the derivation)."""
+        stash = ctx.get("stash")
+        if stash is None:
+            raise L.MarginHeadError("VPLArcFace needs the stash backward (fixed logit scale with s*log2(e)*2 <= 200)")
+        dev = stash.device
+        B, B_pad, C_pad, Cn = ctx["B"], ctx["B_pad"], ctx["C_pad"], self.C
+        st = _stream()
+        rowp, rowout, w_hat, label_local = ctx["rowp"], ctx["rowout"], ctx["w_hat"], ctx["label_local"]
+        xs = self._buf("xs", (B_pad, L.D), torch.bfloat16, dev)
+        rho = self._buf("rho", (B_pad,), torch.float32, dev)
+        gty = self._buf("gty", (B_pad,), torch.float32, dev)
+        L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
+               _ptr(xs), _ptr(rho), _ptr(gty), st)
+        dx = dW = None
+        if need_dx:
+            ns = C.c_int(0)
+            L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), st)
+            part = self._buf("dxhat_part", (ns.value, B_pad, L.D), torch.float32, dev)
+            L.call("mh_tc_backward_dx", _ptr(stash), B_pad, C_pad, _ptr(ctx["w_gemm"]), _ptr(part), C.byref(ns), st)
+            full = self._buf("dxhat_full", (1, B_pad, L.D), torch.float32, dev)
+            # gty already carries (1 - a_y): the target column reaches x^ through w^_y only
+            L.call("mh_stash_dx_combine", _ptr(part), ns.value, B_pad * L.D, _ptr(rho), _ptr(gty), _ptr(label_local),
+                   _ptr(w_hat), B, _ptr(full), st)
+            dx = self._finish_dx(ctx, full, 1, B_pad * L.D, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
+        if need_dw:
+            dwh = self._buf("dw_hat_raw", (C_pad, L.D), torch.float32, dev)
+            L.call("mh_tc_backward_dw", _ptr(stash), B_pad, C_pad, _ptr(xs), _ptr(dwh), st)
+            dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
+            L.call("mh_norm_backward_w", _ptr(dwh), _ptr(w_hat), _ptr(None), _ptr(ctx["inv_norm"]), _ptr(gscal), Cn,
+                   self.layout, _ptr(dW), ctx["ld"], st)
+            dW.mul_((1.0 - ctx["vpl_alpha"]).unsqueeze(1))          # the normalise-backward is linear in dw^
+            L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
+                   _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
         return dx, dW
 
     def _finish_dx(self, ctx, part, n_split, split_stride, gscal, aux0, aux1):

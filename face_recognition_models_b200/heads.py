@@ -311,8 +311,71 @@ class MagFace(_MarginHeadBase):
                           l_a=l_a, u_a=u_a)
 
 
+class VPLArcFace(_MarginHeadBase):
+    """criterion.py:619-762 (VPL-ArcFace, virtual proxies from a per-class feature memory).
+
+    Every non-target cosine of the reference, (1 - a_j) x^.w^_j + a_j x^.m^_j with a_j = lamda * 1[life_j > 0], is the
+    cosine against the mixed class vector v_j = (1 - a_j) w^_j + a_j m^_j, so the head runs the same fused tensor-core
+    pipeline on v (``mh_vpl_mix``); the target column, (1 - a_y) x^.w^_y + a_y, is a per-row term.  Supported through
+    ``fused_loss`` on the tensor-core path in stash mode (s <= 69); the materialised 4-tuple is not built for this head.
+    """
+    family, layout, param_name = "vpl_arcface", "CD", "weight"
+
+    def __init__(self, feat_dim: int, num_class: int, s: float = 64.0, m: float = 0.50, easy_margin: bool = True,
+                 lamda: float = 0.15, delta: int = 100, device_id=None):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.feat_dim, self.num_class, self.s, self.m = feat_dim, num_class, s, m
+        self.easy_margin, self.lamda, self.delta, self.device_id = easy_margin, lamda, delta, device_id
+        self.weight = nn.Parameter(torch.empty(num_class, feat_dim))
+        nn.init.xavier_uniform_(self.weight)
+        self.register_buffer("mem", torch.zeros(num_class, feat_dim))
+        self.register_buffer("life", torch.zeros(num_class))
+        self.register_buffer("cos_m", torch.tensor(math.cos(m), dtype=torch.float32))
+        self.register_buffer("sin_m", torch.tensor(math.sin(m), dtype=torch.float32))
+        self.register_buffer("th", torch.tensor(math.cos(math.pi - m), dtype=torch.float32))
+        self.register_buffer("mm", torch.tensor(math.sin(math.pi - m) * m, dtype=torch.float32))
+        self.norm_training_flag = True
+        self._init_engine(num_class, s=s, m=m, easy_margin=int(bool(easy_margin)))
+
+    def change_training_mode(self, flag: bool):
+        """Toggle memory-based proxy learning (criterion.py:677-679)."""
+        self.norm_training_flag = flag
+
+    @torch.no_grad()
+    def _update_memory(self, feats: torch.Tensor, labels: torch.Tensor):
+        """criterion.py:703-717, without the Python loop over classes: mem[c] = mean of the batch's raw features of class c,
+        life[c] = delta for the classes present, then every lifetime decays by one."""
+        uniq, inv = torch.unique(labels, return_inverse=True)
+        sums = torch.zeros(uniq.numel(), feats.shape[1], dtype=torch.float32, device=feats.device)
+        sums.index_add_(0, inv, feats.float())
+        cnt = torch.bincount(inv, minlength=uniq.numel()).clamp_min(1).unsqueeze(1)
+        mean = sums / cnt
+        if feats.dtype != torch.float32:
+            mean = mean.to(feats.dtype).float()              # the reference takes the mean in the features' dtype
+        self.mem[uniq] = mean
+        self.life[uniq] = float(self.delta)
+        self.life.sub_(1.0)
+
+    def fused_loss(self, feats: torch.Tensor, labels: torch.Tensor) -> FusedOutput:
+        self._check(feats, labels)
+        if self.norm_training_flag:
+            self._update_memory(feats.detach(), labels)
+            self._engine.vpl = dict(mem=self.mem, life=self.life, lamda=float(self.lamda))
+        else:
+            self._engine.vpl = None
+        out = FusedMarginLossFn.apply(feats, self._param(), labels, self._engine, self._mh_state, None, True,
+                                      torch.is_grad_enabled())
+        return FusedOutput(*out)
+
+    def forward(self, feats: torch.Tensor, labels: torch.Tensor):
+        raise NotImplementedError("VPLArcFace is available through fused_loss(feats, labels); the materialised "
+                                  "[pre, logits] 4-tuple of criterion.py:762 is not built for this head")
+
+
 HEAD_CLASSES = dict(
     arcface=ArcFace, cosface=CosFace, sphereface=SphereFace, mv_am=MV_Softmax, mv_arc=MV_Softmax,
     curricularface=CurricularFace, adaface=AdaFace, elastic_cos=ElasticCosFace, elastic_arc=ElasticArcFace,
-    magface=MagFace,
+    magface=MagFace, vpl_arcface=VPLArcFace,
 )

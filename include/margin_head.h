@@ -45,7 +45,8 @@ typedef enum mh_family {
   MH_ADAFACE = 6,                /* criterion.py:795  */
   MH_ELASTIC_COS = 7,            /* criterion.py:951  */
   MH_ELASTIC_ARC = 8,            /* criterion.py:1054 */
-  MH_MAGFACE = 9                 /* criterion.py:1178 */
+  MH_MAGFACE = 9,                /* criterion.py:1178 */
+  MH_VPL_ARC = 10                /* criterion.py:619 (VPLArcFace: memory-bank virtual proxies) */
 } mh_family;
 
 typedef enum mh_layout {
@@ -280,6 +281,17 @@ int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, const float*
 
 /* gscal[0] = upstream_grad(loss_id) / B_total, gscal[1] = upstream_grad(loss_g): device floats so
  * that a GradScaler-scaled backward (model_utils.py:185) needs no host sync. */
+
+/* ---- VPL-ArcFace (criterion.py:619-762) ------------------------------------------------------------------ */
+
+/* Mixed class vectors of the virtual-proxy head: with a_j = lamda * 1[life_j > 0] (life AFTER this step's decay,
+ * criterion.py:716-717), every non-target cosine of the reference is x^_i . v_j with
+ *     v_j = (1 - a_j) * w^_j + a_j * mem_j / max(|mem_j|, 1e-12)                       (criterion.py:720-724)
+ * so the B x C GEMM runs on v (bf16 [C_pad, 512], rows >= C zero) instead of w^.  alpha_out[j] = a_j (fp32 [C]); the
+ * interpolation weights are formed in fp32 exactly as the reference's float32 active_mask does.  One warp per class;
+ * HBM-bound: 2*d (w^ bf16) + 4*d (mem fp32) bytes read, 2*d written per class. */
+int mh_vpl_mix(const void* w_hat_bf16, const float* mem, const float* life, float lamda, int64_t C, int64_t C_pad,
+               void* v_bf16, float* alpha_out, void* stream);
 
 /* ---- pair verification (the device-side piece of the LFW evaluator) ------------------- */
 

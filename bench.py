@@ -216,8 +216,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"                # keep NCCL's version banner off stdout (one JSON line)
+        # keep NCCL's version banner / debug lines off stdout (rank 0 prints exactly one JSON line there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     Cn, B = args.C, args.B
     peaks = load_peaks()
@@ -279,7 +279,7 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         out = step_resident()
     torch.cuda.synchronize()
-    loss_val = float(out.loss)
+    loss_val = float(out.loss.detach())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:

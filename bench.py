@@ -216,11 +216,14 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep NCCL's version banner / debug lines off stdout (rank 0 prints exactly one JSON line there)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     Cn, B = args.C, args.B
     peaks = load_peaks()
+    # Library banners (NCCL prints its version on stdout at communicator creation) must not precede the JSON line:
+    # route fd 1 to stderr for the duration of the run and restore it just before the result is printed.
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
 
     if world > 1:
         head = pkg.ShardedMarginHead("arcface", Cn, s=64.0, m=0.5, easy_margin=False).to(dev)
@@ -385,7 +388,10 @@ def run_b200(args):
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "alt_backward": alt,
             "clocks": sampler.summary() if sampler else None,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -156,3 +156,51 @@ class ShardedMarginHead(nn.Module):
         return FusedOutput(*out)
 
     forward = fused_loss
+
+    # ---- checkpoint interchange with the unsharded reference head ---------------------------
+    def _class_major(self, w: torch.Tensor) -> torch.Tensor:
+        """View a parameter (or shard) with the class index first: [C, D] as is, [D, C] transposed."""
+        return w if self.local.layout == "CD" else w.t()
+
+    @torch.no_grad()
+    def load_full_parameter(self, full: torch.Tensor):
+        """Scatter a full reference parameter (``weight [C, D]`` / ``kernel [D, C]``, e.g. ``checkpoint['model_state_dict']
+        ['arcface.weight']`` saved by model_utils.py:43-60) into this rank's shard.  Every rank passes the same tensor."""
+        C_ = self.num_classes
+        want = (C_, L.D) if self.local.layout == "CD" else (L.D, C_)
+        if tuple(full.shape) != want:
+            raise ValueError(f"expected the full parameter of shape {want}, got {tuple(full.shape)}")
+        shard = self._class_major(full)[self.c_begin:self.c_end]
+        self._class_major(self.shard_parameter().data).copy_(shard.to(self.shard_parameter().device))
+
+    @torch.no_grad()
+    def gather_full_parameter(self) -> torch.Tensor:
+        """All-gather the shards back into the reference parameter layout (on every rank): what the unsharded head's
+        ``state_dict()`` holds under ``weight`` / ``kernel``, so a checkpoint written from it loads into the reference."""
+        w = self._class_major(self.shard_parameter().data).contiguous()
+        if self.comm.world == 1:
+            full = w.clone()
+        else:
+            per = (self.num_classes + self.comm.world - 1) // self.comm.world
+            pad = torch.zeros((per, L.D), dtype=w.dtype, device=w.device)
+            pad[:w.shape[0]] = w                                   # the last shard may be ragged
+            out = torch.empty((self.comm.world * per, L.D), dtype=w.dtype, device=w.device)
+            dist.all_gather_into_tensor(out, pad, group=self.comm.group)
+            full = out[:self.num_classes]
+        return full if self.local.layout == "CD" else full.t().contiguous()
+
+    def full_state_dict(self):
+        """``state_dict`` of the equivalent unsharded reference head: the gathered parameter plus the head's buffers
+        (CurricularFace ``t``, AdaFace ``batch_mean`` / ``batch_std``; identical on every rank)."""
+        sd = {self.local.param_name: self.gather_full_parameter()}
+        for k, v in self.local.state_dict().items():
+            if k != self.local.param_name:
+                sd[k] = v.clone()
+        return sd
+
+    def load_full_state_dict(self, sd):
+        self.load_full_parameter(sd[self.local.param_name])
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k != self.local.param_name:
+                    getattr(self.local, k).copy_(v)

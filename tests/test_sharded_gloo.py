@@ -124,3 +124,52 @@ def test_shard_range_partitions_classes():
         for a, b in zip(ranges, ranges[1:]):
             assert a[1] == b[0]
         assert sum(e - b for b, e in ranges) == Cn
+
+
+def _ckpt_worker(rank, world, port, fam, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import face_recognition_models_b200 as pkg
+        Cn = 37                                                  # ragged: shards of 19 and 18 classes
+        kw = dict(arcface=dict(s=64.0, m=0.5, easy_margin=False), curricularface=dict(m=0.5, s=64.0, momentum=0.01))[fam]
+        torch.manual_seed(123)                                   # same "reference checkpoint" on every rank
+        ref = pkg.HEAD_CLASSES[fam](512, Cn, **kw)
+        sd_ref = {k: v.clone() for k, v in ref.state_dict().items()}
+        if fam == "curricularface":
+            sd_ref["t"].fill_(0.37)
+        head = pkg.ShardedMarginHead(fam, Cn, **kw)
+        head.load_full_state_dict(sd_ref)
+        b, e = head.c_begin, head.c_end
+        full = sd_ref[head.local.param_name]
+        mine = full[b:e] if head.local.layout == "CD" else full[:, b:e]
+        assert torch.equal(head.shard_parameter().data, mine)
+        back = head.full_state_dict()
+        assert set(back) == set(sd_ref)
+        for k in sd_ref:
+            assert torch.equal(back[k], sd_ref[k]), k
+        ref2 = pkg.HEAD_CLASSES[fam](512, Cn, **kw)
+        ref2.load_state_dict(back)                               # the gathered dict loads into the unsharded head
+        q.put((rank, "ok"))
+    except Exception as ex:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fam", ["arcface", "curricularface"])
+def test_checkpoint_interchange_with_unsharded_head(fam):
+    """a reference-style state_dict scatters into the class shards and gathers back unchanged."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ckpt_worker, args=(r, world, port, fam, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

@@ -222,7 +222,10 @@ class CurricularFace(_MarginHeadBase):
         self._mh_state[0:1].copy_(self.t.to(torch.float32))
 
     def _pull_state(self):
-        self.t = self._mh_state[0:1].clone()
+        # in place (the reference rebinds self.t, criterion.py:572): the buffer keeps its address, so a CUDA-graph replay
+        # of the step reads and writes the live state
+        with torch.no_grad():
+            self.t.copy_(self._mh_state[0:1])
 
 
 class AdaFace(_MarginHeadBase):
@@ -248,8 +251,9 @@ class AdaFace(_MarginHeadBase):
         self._mh_state[2:3].copy_(self.batch_std.to(torch.float32))
 
     def _pull_state(self):
-        self.batch_mean = self._mh_state[1:2].clone()
-        self.batch_std = self._mh_state[2:3].clone()
+        with torch.no_grad():                          # in place, see CurricularFace._pull_state
+            self.batch_mean.copy_(self._mh_state[1:2])
+            self.batch_std.copy_(self._mh_state[2:3])
 
 
 class _ElasticBase(_MarginHeadBase):

@@ -2,6 +2,7 @@
 // and compute the per-row margin terms.  Replaces F.normalize / torch.norm / the target gather
 // of the reference heads (criterion.py:65,95,173-174,263-264,400-404,417,538-542,552,860-864,...).
 #include "common.cuh"
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------------
 // prologue_w, layout CD: W [C, 512] row-major. One warp per class; 16 B vector loads, 8 B bf16 stores.
@@ -57,10 +58,18 @@ __global__ void __launch_bounds__(256) prologue_w_dc_kernel(const float* __restr
   const int64_t c0 = (int64_t)blockIdx.x * PW_TC;
   const int64_t c = c0 + tx;
   float ss = 0.f;
-  for (int d = ty; d < MH_D; d += 8) {
-    float v = (c < C) ? __ldg(W + (int64_t)d * ld + c) : 0.f;
-    slab[d * 33 + tx] = v;
-    ss += v * v;
+  // 16 independent 128-byte row loads in flight per warp (the loop was latency-bound at the compiler's unroll of 4:
+  // 2.6 TB/s; HBM needs ~40 KB in flight per SM)
+#pragma unroll 1
+  for (int d0 = ty; d0 < MH_D; d0 += 8 * 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = (c < C) ? __ldg(W + (int64_t)(d0 + 8 * u) * ld + c) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      slab[(d0 + 8 * u) * 33 + tx] = v[u];
+      ss += v[u] * v[u];
+    }
   }
   part[ty][tx] = ss;
   __syncthreads();
@@ -78,17 +87,81 @@ __global__ void __launch_bounds__(256) prologue_w_dc_kernel(const float* __restr
     const int64_t row = c0 + r;
     if (row >= C_pad) continue;
     const float inv = (row < C) ? invs[r] : 0.f;
+    // two consecutive d per lane: the column read of the [d][33] slab is 2-way bank-conflicted (4-way with four),
+    // and a warp still stores full 128-byte lines of bf16
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int d = (tx + 32 * k) * 4;
-      float4 o = make_float4(slab[(d + 0) * 33 + r] * inv, slab[(d + 1) * 33 + r] * inv,
-                             slab[(d + 2) * 33 + r] * inv, slab[(d + 3) * 33 + r] * inv);
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&p0);
-      pk.y = *reinterpret_cast<uint32_t*>(&p1);
-      reinterpret_cast<uint2*>(what + row * MH_D)[tx + 32 * k] = pk;
-      if (what32 && row < C) reinterpret_cast<float4*>(what32 + row * MH_D)[tx + 32 * k] = o;
+    for (int k = 0; k < 8; ++k) {
+      const int d = 2 * tx + 64 * k;
+      const float2 o = make_float2(slab[d * 33 + r] * inv, slab[(d + 1) * 33 + r] * inv);
+      *reinterpret_cast<__nv_bfloat162*>(what + row * MH_D + d) = __floats2bfloat162_rn(o.x, o.y);
+      if (what32 && row < C) *reinterpret_cast<float2*>(what32 + row * MH_D + d) = o;
+    }
+  }
+}
+
+// Same slab kernel for 16-byte-aligned rows (ld % 4 == 0, e.g. C = 2,000,000): one LDG.128 covers 4 d-rows x 32 classes
+// (8 lanes x 16 B per row), 8 of them in flight per warp = 4 KB, 96 KB per SM at 3 resident blocks.
+__global__ void __launch_bounds__(256) prologue_w_dc4_kernel(const float* __restrict__ W, int64_t C, int64_t ld,
+                                                             __nv_bfloat16* __restrict__ what, int64_t C_pad,
+                                                             float* __restrict__ what32, float* __restrict__ inv_norm) {
+  extern __shared__ float slab[];            // [512][33]
+  __shared__ float part[8][PW_TC];
+  __shared__ float invs[PW_TC];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r4 = tx >> 3, q = tx & 7;        // row within the group of 4, float4 index within the 32-class row segment
+  const int64_t c0 = (int64_t)blockIdx.x * PW_TC;
+  const int64_t cq = c0 + 4 * q;
+  float ss4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int it0 = 0; it0 < 16; it0 += 16) {      // all 16 row groups of the warp in flight at once (8 KB per warp)
+    float4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int d = 4 * (ty + 8 * (it0 + u)) + r4;
+      // C % 4 == 0, so a float4 is either entirely inside [0, C) or entirely outside
+      v[u] = (cq < C) ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)d * ld + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int d = 4 * (ty + 8 * (it0 + u)) + r4;
+      float* dst = slab + d * 33 + 4 * q;
+      dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+      ss4[0] += v[u].x * v[u].x; ss4[1] += v[u].y * v[u].y; ss4[2] += v[u].z * v[u].z; ss4[3] += v[u].w * v[u].w;
+    }
+  }
+  // sum over the 4 row groups of the warp (lane bits 3, 4), then over the 8 warps
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    ss4[e] += __shfl_xor_sync(0xffffffffu, ss4[e], 8);
+    ss4[e] += __shfl_xor_sync(0xffffffffu, ss4[e], 16);
+  }
+  if (r4 == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) part[ty][4 * q + e] = ss4[e];
+  }
+  __syncthreads();
+  const int64_t c = c0 + tx;
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][tx];
+    float inv = 1.f / fmaxf(sqrtf(t), 1e-12f);
+    invs[tx] = inv;
+    if (c < C) inv_norm[c] = inv;
+  }
+  __syncthreads();
+  for (int r = ty; r < PW_TC; r += 8) {
+    const int64_t row = c0 + r;
+    if (row >= C_pad) continue;
+    const float inv = (row < C) ? invs[r] : 0.f;
+    // two consecutive d per lane: the column read of the [d][33] slab is 2-way bank-conflicted (4-way with four),
+    // and a warp still stores full 128-byte lines of bf16
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int d = 2 * tx + 64 * k;
+      const float2 o = make_float2(slab[d * 33 + r] * inv, slab[(d + 1) * 33 + r] * inv);
+      *reinterpret_cast<__nv_bfloat162*>(what + row * MH_D + d) = __floats2bfloat162_rn(o.x, o.y);
+      if (what32 && row < C) *reinterpret_cast<float2*>(what32 + row * MH_D + d) = o;
     }
   }
 }
@@ -116,10 +189,14 @@ extern "C" int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, 
     const int smem = MH_D * 33 * sizeof(float);
     if (!attr_set) {
       MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set = true;
     }
     dim3 grid((unsigned)((C + PW_TC - 1) / PW_TC));
-    prologue_w_dc_kernel<<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
+    if (ld % 4 == 0 && C % 4 == 0 && ((uintptr_t)W & 15) == 0)
+      prologue_w_dc4_kernel<<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
+    else
+      prologue_w_dc_kernel<<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
     const int64_t covered = (int64_t)grid.x * PW_TC;
     if (covered < C_pad) {
       int64_t n = (C_pad - covered) * MH_D;

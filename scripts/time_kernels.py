@@ -5,14 +5,19 @@ import torch
 import face_recognition_models_b200 as pkg
 from face_recognition_models_b200 import _lib as L
 B, Cn = 1024, int(os.environ.get("C", 2_000_000))
-head = pkg.ArcFace(512, Cn, s=64.0, m=0.5, easy_margin=False).cuda()
+FAM = os.environ.get("FAM", "arcface")
+head = {"arcface": lambda: pkg.ArcFace(512, Cn, s=64.0, m=0.5, easy_margin=False),
+        "cosface": lambda: pkg.CosFace(512, Cn, s=64.0, m=0.35),
+        "magface": lambda: pkg.MagFace(512, Cn),
+        "curricularface": lambda: pkg.CurricularFace(512, Cn),
+        "sphereface": lambda: pkg.SphereFace(512, Cn, m=2)}[FAM]().cuda()
 g = torch.Generator(device="cuda").manual_seed(4)
 with torch.no_grad():
-    head.weight.normal_(0, 0.01, generator=g)
+    head._param().normal_(0, 0.01, generator=g)
 x = torch.randn(B, 512, device="cuda", generator=g)
 y = torch.randint(0, Cn, (B,), device="cuda", generator=g)
 def step():
-    xg = x.detach().requires_grad_(True); head.weight.grad = None
+    xg = x.detach().requires_grad_(True); head._param().grad = None
     out = head.fused_loss(xg, y); out.loss.backward(); return out
 def measure(tag):
     for _ in range(5): step()

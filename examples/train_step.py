@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--classes", type=int, default=10575)
     ap.add_argument("--backbone", default="resnet50")
     ap.add_argument("--lambda_g", type=float, default=0.0)
+    ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--init_scale", type=float, default=1024.0)
     ap.add_argument("--lfw_pairs", type=int, default=6000, help="synthetic verification pairs (0 = skip)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -52,8 +54,10 @@ def main():
     else:
         head = pkg.ArcFace(512, a.classes, s=64.0, m=0.5, easy_margin=False).to(dev)
         head_params = list(head.parameters())
-    opt = torch.optim.SGD(list(backbone.parameters()) + head_params, lr=0.1, momentum=0.9, weight_decay=5e-4)
-    scaler = torch.amp.GradScaler("cuda")
+    opt = torch.optim.SGD(list(backbone.parameters()) + head_params, lr=a.lr, momentum=0.9, weight_decay=5e-4)
+    # model_utils.py:559 uses the default GradScaler (init_scale 65536): with fp16 features its first steps overflow and
+    # are skipped while the scale halves; start lower so that a short demo run shows the loss moving
+    scaler = torch.amp.GradScaler("cuda", init_scale=a.init_scale)
     images = torch.randn(a.batch, 3, 112, 112, device=dev)
     target = torch.randint(0, a.classes, (a.batch,), device=dev)
     for step in range(a.steps):

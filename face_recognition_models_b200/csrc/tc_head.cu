@@ -79,7 +79,6 @@ struct TcArgs {
   float* rsum;                 // r_j [C_pad]: DX (stash) accumulates into it, DW fused reads it
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
-  int side_debug;              // experiment: 1 = loads + release only (no math)
   const __nv_bfloat16* w_hat;  // DW fused
   const float* inv_norm;       // DW fused
   const float* gscal;          // DW fused
@@ -550,7 +549,6 @@ __device__ __forceinline__ void flush_tile(const uint8_t* stg, int lane, uint8_t
     if (rr < rows_ok) *reinterpret_cast<uint4*>(dst + (int64_t)rr * pitch_bytes + (lane & 7) * 16) = val;
   }
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Walk the NCHUNK 32-column chunks of this thread's accumulator row: the TMEM load of chunk c+1 is in flight while
 // chunk c is processed.  loaded() runs once every TMEM read of the row has completed (before the last chunk's body).
@@ -859,11 +857,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_local(bar_rdone + 8 * side_stage);
-            if (a.side_debug == 1) {
-              if ((q4[0].x ^ q4[1].x ^ q4[2].x ^ q4[3].x) == 0x12345678u) atomicAdd(a.rsum, 1.f);
-              if (++side_stage == STAGES) { side_stage = 0; side_phase ^= 1; }
-              continue;
-            }
             float acc8[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc8[e] = 0.f;
@@ -1229,7 +1222,6 @@ static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad,
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
   a.rho = rho; a.side_kappa = kappa; a.side_inv_s2 = inv_s2; a.rsum = r_colsum;
-  { const char* e = getenv("MH_DX_SIDE_DEBUG"); a.side_debug = e ? atoi(e) : 0; }
   if (rho) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
   return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }

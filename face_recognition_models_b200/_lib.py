@@ -71,7 +71,7 @@ SIGNATURES = {
     "mh_merge_stats": [_vp, _i64, _i64, _i64, _vp, _vp, _vp],
     "mh_finalize_rows": [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp],
     "mh_norm_backward_x": [_vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _vp],
-    "mh_norm_backward_w": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
+    "mh_norm_backward_w": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
 }
 _RESTYPES = {"mh_version": C.c_char_p, "mh_last_error": C.c_char_p, "mh_fwd_num_tiles": C.c_int64}
 EXPORTED = sorted(list(SIGNATURES) + ["mh_version", "mh_last_error", "mh_fwd_num_tiles", "mh_tc_schedule_tiles"])

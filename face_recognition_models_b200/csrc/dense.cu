@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(256) norm_backward_w_cd_kernel(const float* __
                                                                  const __nv_bfloat16* __restrict__ wb,
                                                                  const float* __restrict__ w32,
                                                                  const float* __restrict__ inv_norm,
-                                                                 const float* __restrict__ gscal, int64_t C,
+                                                                 const float* __restrict__ gscal,
+                                                                 const float* __restrict__ class_scale, int64_t C,
                                                                  float* __restrict__ dW, int64_t ld) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(256) norm_backward_w_cd_kernel(const float* __
     dot += g[k].x * w[k].x + g[k].y * w[k].y + g[k].z * w[k].z + g[k].w * w[k].w;
   }
   dot = warp_sum(dot);
-  const float sc = gscal[0] * inv_norm[row];
+  const float sc = gscal[0] * inv_norm[row] * (class_scale ? class_scale[row] : 1.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float4 o = make_float4((g[k].x - w[k].x * dot) * sc, (g[k].y - w[k].y * dot) * sc, (g[k].z - w[k].z * dot) * sc,
@@ -460,7 +461,8 @@ __global__ void __launch_bounds__(256) norm_backward_w_dc_kernel(const float* __
                                                                  const __nv_bfloat16* __restrict__ wb,
                                                                  const float* __restrict__ w32,
                                                                  const float* __restrict__ inv_norm,
-                                                                 const float* __restrict__ gscal, int64_t C,
+                                                                 const float* __restrict__ gscal,
+                                                                 const float* __restrict__ class_scale, int64_t C,
                                                                  float* __restrict__ dW, int64_t ld) {
   extern __shared__ float slab[];            // [512][33]
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(256) norm_backward_w_dc_kernel(const float* __
       }
     }
     dot = warp_sum(dot);
-    const float sc = (row < C) ? gz * inv_norm[row] : 0.f;
+    const float sc = (row < C) ? gz * inv_norm[row] * (class_scale ? class_scale[row] : 1.f) : 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int d = (tx + 32 * k) * 4;
@@ -499,15 +501,15 @@ __global__ void __launch_bounds__(256) norm_backward_w_dc_kernel(const float* __
 }
 
 extern "C" int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, const float* w_hat32,
-                                  const float* inv_norm, const float* gscal, int64_t C, int layout, float* dW,
-                                  int64_t ld, void* stream) {
+                                  const float* inv_norm, const float* gscal, const float* class_scale, int64_t C,
+                                  int layout, float* dW, int64_t ld, void* stream) {
   MH_CHECK_ARG(dw_hat && inv_norm && gscal && dW, "null pointer");
   MH_CHECK_ARG((w_hat_bf16 != nullptr) != (w_hat32 != nullptr), "exactly one of w_hat_bf16 / w_hat32");
   cudaStream_t st = (cudaStream_t)stream;
   if (layout == MH_LAYOUT_CD) {
     MH_CHECK_ARG(ld % 4 == 0 && ((uintptr_t)dW & 15) == 0, "dW must be 16-byte aligned");
     norm_backward_w_cd_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(dw_hat, (const __nv_bfloat16*)w_hat_bf16, w_hat32,
-                                                                      inv_norm, gscal, C, dW, ld);
+                                                                      inv_norm, gscal, class_scale, C, dW, ld);
   } else if (layout == MH_LAYOUT_DC) {
     static bool attr_set = false;
     const int smem = MH_D * 33 * sizeof(float);
@@ -516,7 +518,7 @@ extern "C" int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, c
       attr_set = true;
     }
     norm_backward_w_dc_kernel<<<(unsigned)((C + 31) / 32), 256, smem, st>>>(dw_hat, (const __nv_bfloat16*)w_hat_bf16,
-                                                                          w_hat32, inv_norm, gscal, C, dW, ld);
+                                                                          w_hat32, inv_norm, gscal, class_scale, C, dW, ld);
   } else {
     MH_CHECK_ARG(false, "unknown layout");
   }

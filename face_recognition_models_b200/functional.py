@@ -316,9 +316,10 @@ class HeadEngine:
             dwh = self._buf("dw_hat_raw", (C_pad, L.D), torch.float32, dev)
             L.call("mh_tc_backward_dw", _ptr(stash), B_pad, C_pad, _ptr(xs), _ptr(dwh), st)
             dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
-            L.call("mh_norm_backward_w", _ptr(dwh), _ptr(w_hat), _ptr(None), _ptr(ctx["inv_norm"]), _ptr(gscal), Cn,
-                   self.layout, _ptr(dW), ctx["ld"], st)
-            dW.mul_((1.0 - ctx["vpl_alpha"]).unsqueeze(1))          # the normalise-backward is linear in dw^
+            beta = self._buf("vpl_beta", (Cn,), torch.float32, dev)
+            torch.sub(1.0, ctx["vpl_alpha"], out=beta)               # 1 - a_j; the normalise-backward is linear in dw^
+            L.call("mh_norm_backward_w", _ptr(dwh), _ptr(w_hat), _ptr(None), _ptr(ctx["inv_norm"]), _ptr(gscal), _ptr(beta),
+                   Cn, self.layout, _ptr(dW), ctx["ld"], st)
             L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
                    _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
         return dx, dW
@@ -363,7 +364,7 @@ class HeadEngine:
             L.call("mh_sgemm_strided", Cn, L.D, B, _ptr(dc), 1, Cn, _ptr(ctx["x_hat32"]), L.D, 1, _ptr(dwh), L.D, st)
             dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
             L.call("mh_norm_backward_w", _ptr(dwh), _ptr(None), _ptr(ctx["w_hat32"]), _ptr(ctx["inv_norm"]), _ptr(gscal),
-                   Cn, self.layout, _ptr(dW), ctx["ld"], st)
+                   _ptr(None), Cn, self.layout, _ptr(dW), ctx["ld"], st)
         return dx, dW
 
     # -- backward of the compat (materialised logits) outputs ---------------------------------------

@@ -273,11 +273,12 @@ int mh_norm_backward_x(const float* dxhat, int n_split, int64_t split_stride, co
                        const float* aux1, const float* gscal, int64_t B, void* dx, int x_dtype,
                        void* stream);
 
-/* dW_j = g * (dw^_j - w^_j (w^_j . dw^_j)) / |w_j|, written in the parameter's own layout
- * (ld = row pitch of dW).  w_hat given as bf16 [C_pad,512] or fp32 [C,512] (exactly one non-NULL). */
+/* dW_j = g * k_j * (dw^_j - w^_j (w^_j . dw^_j)) / |w_j|, written in the parameter's own layout
+ * (ld = row pitch of dW).  w_hat given as bf16 [C_pad,512] or fp32 [C,512] (exactly one non-NULL).
+ * class_scale k [C] may be NULL (= 1): VPL-ArcFace passes 1 - a_j (criterion.py:724). */
 int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, const float* w_hat32,
-                       const float* inv_norm, const float* gscal, int64_t C, int layout, float* dW,
-                       int64_t ld, void* stream);
+                       const float* inv_norm, const float* gscal, const float* class_scale, int64_t C, int layout,
+                       float* dW, int64_t ld, void* stream);
 
 /* gscal[0] = upstream_grad(loss_id) / B_total, gscal[1] = upstream_grad(loss_g): device floats so
  * that a GradScaler-scaled backward (model_utils.py:185) needs no host sync. */

@@ -69,7 +69,8 @@ SIGNATURES = {
     "mh_dense_forward": [_cfgp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_dense_backward_dc": [_cfgp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_merge_stats": [_vp, _i64, _i64, _i64, _vp, _vp, _vp],
-    "mh_finalize_rows": [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp],
+    "mh_finalize_rows": [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp],
+    "mh_make_gscal": [_vp, _vp, _i64, _vp, _vp],
     "mh_norm_backward_x": [_vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _vp],
     "mh_norm_backward_w": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
 }

@@ -280,7 +280,8 @@ extern "C" int mh_merge_stats(const float* stats_in, int64_t n_parts, int64_t B,
 __global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __restrict__ stats, int64_t lds_,
                                                              const float* __restrict__ rowp, int64_t ldp, int64_t B,
                                                              int64_t B_total, int sphere, float* __restrict__ rowout,
-                                                             int64_t ldo, float* __restrict__ scalars) {
+                                                             int64_t ldo, float* __restrict__ scalars,
+                                                             const float* __restrict__ state) {
   __shared__ double sh[3][32];
   double sl = 0.0, s1 = 0.0, s5 = 0.0;
   for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
@@ -315,15 +316,17 @@ __global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __rest
     scalars[0] = (float)(t[0] / (double)B_total);
     scalars[1] = (float)(100.0 * t[1] / (double)B_total);
     scalars[2] = (float)(100.0 * t[2] / (double)B_total);
+    scalars[3] = state ? state[3] : 0.f;                 // loss_g of this forward (MagFace), else 0
   }
 }
 
 extern "C" int mh_finalize_rows(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B,
-                                int64_t B_total, int sphere, float* rowout, int64_t ldo, float* scalars, void* stream) {
+                                int64_t B_total, int sphere, float* rowout, int64_t ldo, float* scalars,
+                                const float* state, void* stream) {
   MH_CHECK_ARG(stats && rowp && rowout && scalars, "null pointer");
   MH_CHECK_ARG(B > 0 && B_total >= B && lds_ >= B && ldp >= B && ldo >= B, "bad shape");
   finalize_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stats, lds_, rowp, ldp, B, B_total, sphere, rowout, ldo,
-                                                             scalars);
+                                                             scalars, state);
   MH_LAUNCH_OK();
   return MH_OK;
 }
@@ -522,6 +525,23 @@ extern "C" int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, c
   } else {
     MH_CHECK_ARG(false, "unknown layout");
   }
+  MH_LAUNCH_OK();
+  return MH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gscal = {upstream grad of loss_id / B_total, upstream grad of loss_g}: one tiny launch instead of a chain of
+// framework fill / index kernels, and no host sync under a GradScaler (model_utils.py:185).
+// ------------------------------------------------------------------------------------------------
+__global__ void make_gscal_kernel(const float* __restrict__ g_loss, const float* __restrict__ g_lossg, float inv_b,
+                                  float* __restrict__ gscal) {
+  gscal[0] = (g_loss ? g_loss[0] : 0.f) * inv_b;
+  gscal[1] = g_lossg ? g_lossg[0] : 0.f;
+}
+
+extern "C" int mh_make_gscal(const float* g_loss, const float* g_lossg, int64_t B_total, float* gscal, void* stream) {
+  MH_CHECK_ARG(gscal && B_total > 0, "bad argument");
+  make_gscal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g_loss, g_lossg, 1.f / (float)B_total, gscal);
   MH_LAUNCH_OK();
   return MH_OK;
 }

@@ -212,9 +212,9 @@ class HeadEngine:
             L.call("mh_merge_stats", _ptr(all_stats), self.shard.world, B, B_pad, _ptr(scratch), _ptr(stats), st)
 
         rowout = self._buf("rowout", (L.RO_PLANES, B_pad), torch.float32, dev)
-        scalars = torch.empty(3, dtype=torch.float32, device=dev)
+        scalars = torch.empty(4, dtype=torch.float32, device=dev)      # loss, acc@1, acc@5, loss_g (fresh: returned to the user)
         L.call("mh_finalize_rows", _ptr(stats), B_pad, _ptr(rowp), B_pad, B, B, 1 if self.family == "sphereface" else 0,
-               _ptr(rowout), B_pad, _ptr(scalars), st)
+               _ptr(rowout), B_pad, _ptr(scalars), _ptr(state), st)
         return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=w_hat, w_hat32=w_hat32, inv_norm=inv_norm,
                     x_hat=x_hat, x_hat32=x_hat32, xnorm=xnorm, label_local=label_local, rowp=rowp, rowout=rowout,
                     scalars=scalars, S=S, pre=pre, logits=logits, exact=exact, gen=self._gen, state=state,
@@ -230,10 +230,7 @@ class HeadEngine:
         dev = ctx["x_hat"].device
         B, B_pad, C_pad, Cn = ctx["B"], ctx["B_pad"], ctx["C_pad"], self.C
         st = _stream()
-        gscal = torch.zeros(2, dtype=torch.float32, device=dev)
-        gscal[0] = g_loss.to(torch.float32) / B
-        if g_lossg is not None:
-            gscal[1] = g_lossg.to(torch.float32)
+        gscal = self._gscal(g_loss, g_lossg, B, dev)
         rowp, rowout, state = ctx["rowp"], ctx["rowout"], ctx["state"]
         lse2 = rowout[L.RO["LSE2"]]
         if ctx["exact"]:
@@ -324,6 +321,16 @@ class HeadEngine:
                    _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
         return dx, dW
 
+    def _gscal(self, g_loss, g_lossg, B_total, dev) -> torch.Tensor:
+        """Device scalars {g_loss / B_total, g_lossg} in one launch (no host sync under a GradScaler)."""
+        gscal = torch.empty(2, dtype=torch.float32, device=dev)
+        if g_loss is not None and g_loss.dtype != torch.float32:
+            g_loss = g_loss.float()
+        if g_lossg is not None and g_lossg.dtype != torch.float32:
+            g_lossg = g_lossg.float()
+        L.call("mh_make_gscal", _ptr(g_loss), _ptr(g_lossg), B_total, _ptr(gscal), _stream())
+        return gscal
+
     def _finish_dx(self, ctx, part, n_split, split_stride, gscal, aux0, aux1):
         """Sum split partials (+ cross-rank reduce-scatter when sharded) and apply normalise-backward."""
         B = ctx["B"]
@@ -383,10 +390,7 @@ class HeadEngine:
         S = ctx["S"]
         L.call("mh_dense_backward_dc", C.byref(self.cfg), _ptr(S), Cn, B, Cn, _ptr(ctx["rowp"]), B_pad,
                _ptr(ctx["label_local"]), _ptr(ctx["state"]), _ptr(None), _ptr(dlogits), _ptr(dpre), _ptr(rowaux), st)
-        gscal = torch.zeros(2, dtype=torch.float32, device=dev)
-        gscal[0] = 1.0
-        if g_lossg is not None:
-            gscal[1] = g_lossg.to(torch.float32)
+        gscal = self._gscal(torch.ones((), dtype=torch.float32, device=dev), g_lossg, 1, dev)
         return self._exact_grads(ctx, S, gscal, rowaux[0], rowaux[1], need_dx, need_dw)
 
 
@@ -401,13 +405,9 @@ class FusedMarginLossFn(torch.autograd.Function):
         ctx.engine = engine
         ctx.c = c
         ctx.x_dtype = x.dtype
-        sc = c["scalars"]
-        loss = sc[0].clone()
-        loss_g = state[3].clone()
+        loss, acc1, acc5, loss_g = c["scalars"].unbind(0)           # views of a tensor created by this forward
         norms = c["rowp"][L.RP["NORMS"], :c["B"]].clone().unsqueeze(1)
-        ctx.mark_non_differentiable(norms)
-        acc1, acc5 = sc[1].clone(), sc[2].clone()
-        ctx.mark_non_differentiable(acc1, acc5)
+        ctx.mark_non_differentiable(norms, acc1, acc5)
         return loss, loss_g, acc1, acc5, norms
 
     @staticmethod

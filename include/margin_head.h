@@ -259,9 +259,15 @@ int mh_merge_stats(const float* stats_in, int64_t n_parts, int64_t B, int64_t ld
 
 /* Final per-row results from merged statistics + scalars:
  * rowout [MH_RO_PLANES, ldo]; scalars[0]=mean CE loss, [1]=acc@1 %, [2]=acc@5 % (metrics.py:3-16),
- * computed over rows [0,B) with divisor B_total (global batch, >= B). */
+ * computed over rows [0,B) with divisor B_total (global batch, >= B); scalars[3] = state[3] (loss_g of this forward;
+ * 0 when state is NULL). */
 int mh_finalize_rows(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B,
-                     int64_t B_total, int sphere, float* rowout, int64_t ldo, float* scalars, void* stream);
+                     int64_t B_total, int sphere, float* rowout, int64_t ldo, float* scalars, const float* state,
+                     void* stream);
+
+/* gscal[0] = g_loss[0] / B_total, gscal[1] = g_lossg[0] (NULL pointers read as 0): the device-side upstream-gradient
+ * scalars every backward kernel takes, so that a GradScaler-scaled backward (model_utils.py:185) needs no host sync. */
+int mh_make_gscal(const float* g_loss, const float* g_lossg, int64_t B_total, float* gscal, void* stream);
 
 /* dx = (dxh - x^ (x^.dxh)) / |x| + dn * x^   with dxh = gz * sum_splits dxhat and
  * dn = gz * (AUX0 * DZT_DN + AUX1) + g_lossg * DLG_DN  (autograd of F.normalize + the |x| paths of

@@ -4,17 +4,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import face_recognition_models_b200 as pkg
 from face_recognition_models_b200 import _lib as L
-B, Cn = 1024, int(os.environ.get("C", 2_000_000))
+B, Cn = int(os.environ.get("B", 1024)), int(os.environ.get("C", 2_000_000))
 FAM = os.environ.get("FAM", "arcface")
 head = {"arcface": lambda: pkg.ArcFace(512, Cn, s=64.0, m=0.5, easy_margin=False),
         "cosface": lambda: pkg.CosFace(512, Cn, s=64.0, m=0.35),
         "magface": lambda: pkg.MagFace(512, Cn),
+        "adaface": lambda: pkg.AdaFace(512, Cn),
+        "elastic_arc": lambda: pkg.ElasticArcFace(512, Cn),
+        "elastic_cos": lambda: pkg.ElasticCosFace(512, Cn),
+        "mv_am": lambda: pkg.MV_Softmax(512, Cn, margin_type="am"),
         "curricularface": lambda: pkg.CurricularFace(512, Cn),
         "sphereface": lambda: pkg.SphereFace(512, Cn, m=2)}[FAM]().cuda()
 g = torch.Generator(device="cuda").manual_seed(4)
 with torch.no_grad():
     head._param().normal_(0, 0.01, generator=g)
-x = torch.randn(B, 512, device="cuda", generator=g)
+x = torch.randn(B, 512, device="cuda", generator=g) * 3.0
 y = torch.randint(0, Cn, (B,), device="cuda", generator=g)
 def step():
     xg = x.detach().requires_grad_(True); head._param().grad = None

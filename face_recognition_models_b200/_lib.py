@@ -54,7 +54,7 @@ SIGNATURES = {
     "mh_row_params": [_cfgp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
-    "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
+    "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp],
     "mh_vpl_mix": [_vp, _vp, _vp, C.c_float, _i64, _i64, _vp, _vp, _vp],
     "mh_pair_cosine": [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp],

@@ -76,7 +76,9 @@ struct TcArgs {
   int64_t out_split_stride;
   int fixref;                  // FWD: fixed softmax reference (see mh_tc_fixref_ok); always 1 for FWDS
   float umax;                  // upper bound of u = z / scale over non-target columns (fixref)
-  float* rsum;                 // r_j [C_pad]: DX (stash) accumulates into it, DW fused reads it
+  float* rsum;                 // r_j: BWD_G accumulates [C_pad] (atomics); DX (stash) stores one partial per 128-row block
+                               // ([B_pad/128][C_pad], plain stores: reproducible); DW fused sums rsum_parts partials
+  int rsum_parts;              // DW fused: number of partial planes of rsum (1 for the BWD_G sums)
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
   const __nv_bfloat16* w_hat;  // DW fused
@@ -887,7 +889,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             t += __shfl_xor_sync(0xffffffffu, t, 8);
             t += __shfl_xor_sync(0xffffffffu, t, 16);
             // lane L (< 8) now holds class bit-reversal-free index: value e = (L&4 ? 4:0)|(L&2 ? 2:0)|(L&1 ? 1:0)
-            if (lane < 8) atomicAdd(a.rsum + (int64_t)kb * BK + ew * 8 + lane, t);
+            // every (128-row block, class) pair is produced exactly once: plain store, no atomics, no memset
+            if (lane < 8) a.rsum[(int64_t)(w.m0 / BM) * a.C_pad + (int64_t)kb * BK + ew * 8 + lane] = t;
             if (++side_stage == STAGES) { side_stage = 0; side_phase ^= 1; }
           }
         }
@@ -904,7 +907,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const bool raw = a.raw_dw != 0;
         const bool ok = raw || row < a.C;
         float rj = 0.f, coef = 1.f;
-        if (!raw && row < a.C) { rj = a.rsum[row]; coef = a.gscal[0] * a.inv_norm[row]; }
+        if (!raw && row < a.C) {
+          for (int pp = 0; pp < a.rsum_parts; ++pp) rj += a.rsum[(int64_t)pp * a.C_pad + row];   // fixed order
+          coef = a.gscal[0] * a.inv_norm[row];
+        }
         if (!raw && row >= a.C) coef = 0.f;
         const int rows_ok = raw ? 32 : (int)max((int64_t)0, min((int64_t)32, a.C - ((int64_t)w.m0 + q * 32)));
         const int64_t opitch = raw ? (int64_t)MH_D : a.ld;
@@ -1222,7 +1228,6 @@ static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad,
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
   a.rho = rho; a.side_kappa = kappa; a.side_inv_s2 = inv_s2; a.rsum = r_colsum;
-  if (rho) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
   return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }
 
@@ -1269,7 +1274,7 @@ extern "C" int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pa
 
 extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
                                        const void* w_hat_bf16, const float* inv_norm, const float* r_colsum,
-                                       const float* gscal, int layout, float* dW, int64_t ld, void* stream) {
+                                       int r_parts, const float* gscal, int layout, float* dW, int64_t ld, void* stream) {
   MH_CHECK_ARG(G_bf16 && x_hat_bf16 && w_hat_bf16 && inv_norm && r_colsum && gscal && dW, "null pointer");
   MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0 && C > 0 && C <= C_pad, "bad padded shape");
   MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
@@ -1277,7 +1282,8 @@ extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_
   TcArgs a{};
   a.out = dW; a.raw_dw = 0; a.layout = layout; a.ld = ld;
   a.w_hat = (const __nv_bfloat16*)w_hat_bf16; a.inv_norm = inv_norm; a.gscal = gscal;
-  a.rsum = const_cast<float*>(r_colsum);
+  a.rsum = const_cast<float*>(r_colsum); a.rsum_parts = r_parts;
+  MH_CHECK_ARG(r_parts >= 1, "r_parts must be >= 1");
   if (int e = make_tmap(&a.tmW, w_hat_bf16, C_pad, MH_D, BM)) return e;       // epilogue operand: boxes [64 d][128 classes]
   return launch_dw(G_bf16, B_pad, C, C_pad, x_hat_bf16, a, (cudaStream_t)stream);
 }

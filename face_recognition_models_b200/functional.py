@@ -242,7 +242,8 @@ class HeadEngine:
         stash = ctx.get("stash")
         if self.family == "vpl_arcface":
             return self._backward_vpl(ctx, gscal, need_dx, need_dw)
-        rsum = self._buf("r_colsum", (C_pad,), torch.float32, dev)
+        r_parts = B_pad // L.TILE if stash is not None else 1      # stash: one partial per 128-row block (no atomics)
+        rsum = self._buf("r_colsum", (r_parts, C_pad), torch.float32, dev)
         ns = C.c_int(0)
         L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), st)
         n_split = ns.value
@@ -277,7 +278,7 @@ class HeadEngine:
         if need_dw:
             dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
             L.call("mh_tc_backward_dw_fused", _ptr(G), B_pad, Cn, C_pad, _ptr(xs), _ptr(w_hat), _ptr(ctx["inv_norm"]),
-                   _ptr(rsum), _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], st)
+                   _ptr(rsum), r_parts, _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], st)
             if stash is not None:
                 L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
                        _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)

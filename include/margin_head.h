@@ -190,10 +190,12 @@ int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const vo
                       float* out, int* n_split_host, void* stream);
 
 /* Stash mode: the same GEMM on the stash E' (out = E' . w_hat; scale the rows by rho afterwards, mh_stash_dx_combine).
- * While the tensor cores run, the kernel's idle epilogue warps re-read every E' tile from shared memory and accumulate
- * r_colsum[j] = sum_i rho_i * E'_ij * cos_ij (zeroed first, stream-ordered), with cos_ij = log2(E'_ij)/(s log2e) + ref/(s log2e)
- * recovered from the stash itself: the non-target part of the projection term w^_j . dw^_j that mh_tc_backward_dw_fused
- * needs (the target column's part is added by mh_stash_dw_target). */
+ * While the tensor cores run, the kernel's idle epilogue warps re-read every E' tile from shared memory and store
+ * r_colsum[b][j] = sum_{i in 128-row block b} rho_i * E'_ij * cos_ij for b < B_pad/128 (r_colsum is [B_pad/128, C_pad];
+ * plain stores, every element written once: no atomics, bit-reproducible), with
+ * cos_ij = log2(E'_ij)/(s log2e) + ref/(s log2e) recovered from the stash itself: the non-target part of the projection
+ * term w^_j . dw^_j that mh_tc_backward_dw_fused needs, passed there with r_parts = B_pad/128 (the target column's part
+ * is added by mh_stash_dw_target). */
 int mh_tc_backward_dx_stash(const mh_config* cfg_host, const void* stash_bf16, int64_t B_pad, int64_t C, int64_t C_pad,
                             const void* w_hat_bf16, const float* rho, float* out, float* r_colsum, int* n_split_host,
                             void* stream);
@@ -203,11 +205,12 @@ int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const vo
                       float* dw_hat, void* stream);
 
 /* dw_hat = G^T . x_hat fused with the normalise-backward of W (autograd of F.normalize(self.weight), criterion.py:264):
- * dW_j = gscal[0] * (dw^_j - w^_j * r_j) / |w_j| written straight into the parameter layout (ld = row pitch);
+ * dW_j = gscal[0] * (dw^_j - w^_j * r_j) / |w_j| written straight into the parameter layout (ld = row pitch), with
+ * r_j = sum_{p < r_parts} r_colsum[p * C_pad + j] (1 plane from mh_tc_backward_g, B_pad/128 from mh_tc_backward_dx_stash);
  * replaces mh_tc_backward_dw + mh_norm_backward_w and their 4*C*d-byte dw_hat round trip.  x_hat_bf16 is x^ (recompute
  * mode, G from mh_tc_backward_g) or the rho-scaled rows of mh_stash_prep (stash mode, G = the stash). */
 int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
-                            const void* w_hat_bf16, const float* inv_norm, const float* r_colsum,
+                            const void* w_hat_bf16, const float* inv_norm, const float* r_colsum, int r_parts,
                             const float* gscal, int layout, float* dW, int64_t ld, void* stream);
 
 /* ---- stash backward: O(B*d) helpers (see mh_tc_forward's stash) -------------------------------------- */

@@ -180,6 +180,14 @@ def test_properties_at_scale(pkg, bmode):
     (out2.loss * 8.0).backward()
     assert float(out2.loss) == float(out.loss)                     # deterministic
     assert rel(x.grad, dx1 * 8.0) < 1e-6 and rel(head.weight.grad, dW1 * 8.0) < 1e-6
+    # bit-reproducibility: run the same step again; dx always, dW in stash mode (recompute sums r_j with atomics)
+    x.grad = None
+    head.weight.grad = None
+    out3 = head.fused_loss(x, y)
+    out3.loss.backward()
+    assert torch.equal(x.grad, dx1)
+    if bmode == "auto":
+        assert torch.equal(head.weight.grad, dW1)
 
 
 def test_error_paths(pkg):

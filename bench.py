@@ -209,6 +209,11 @@ def run_b200(args):
     import face_recognition_models_b200 as pkg
     from face_recognition_models_b200 import _lib as L
 
+    # Library banners (NCCL_DEBUG=VERSION prints "NCCL version ..." on stdout at communicator creation) must not
+    # precede the JSON line: route fd 1 to stderr for the duration of the run, restore it to print the result.
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -219,11 +224,6 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     Cn, B = args.C, args.B
     peaks = load_peaks()
-    # Library banners (NCCL prints its version on stdout at communicator creation) must not precede the JSON line:
-    # route fd 1 to stderr for the duration of the run and restore it just before the result is printed.
-    sys.stdout.flush()
-    saved_stdout_fd = os.dup(1)
-    os.dup2(2, 1)
 
     if world > 1:
         head = pkg.ShardedMarginHead("arcface", Cn, s=64.0, m=0.5, easy_margin=False).to(dev)

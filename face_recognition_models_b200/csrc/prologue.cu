@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
                                                          const float* __restrict__ inv_norm,
                                                          __nv_bfloat16* __restrict__ xhat, float* __restrict__ xhat32,
                                                          float* __restrict__ xnorm, float* __restrict__ t_raw,
-                                                         int32_t* __restrict__ label_local) {
+                                                         int32_t* __restrict__ label_local, int strict_labels) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B_pad) return;
@@ -331,7 +331,9 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
   dot = warp_sum(dot);
   if (lane == 0) {
     xnorm[row] = nrm;
-    t_raw[row] = owned ? dot * inv_norm[y] : 0.f;
+    // strict_labels (unsharded head): a label outside [0, C) poisons the row's target cosine, so the loss comes out NaN
+    // instead of silently dropping the target (the reference's one_hot.scatter_ raises a device assert there)
+    t_raw[row] = owned ? dot * inv_norm[y] : (strict_labels ? __int_as_float(0x7fc00000) : 0.f);
     label_local[row] = owned ? (int32_t)y : -1;
   }
 }
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
 extern "C" int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pad, const int64_t* labels,
                              const float* W, int layout, int64_t C, int64_t ld, int64_t c_offset,
                              const float* inv_norm, void* x_hat_bf16, float* x_hat32, float* xnorm, float* t_raw,
-                             int32_t* label_local, void* stream) {
+                             int32_t* label_local, int strict_labels, void* stream) {
   MH_CHECK_ARG(x && labels && W && inv_norm && x_hat_bf16 && x_hat32 && xnorm && t_raw && label_local, "null pointer");
   MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % MH_TILE == 0, "B_pad must be a multiple of 128 and >= B");
   MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
@@ -349,13 +351,13 @@ extern "C" int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pa
   __nv_bfloat16* xh = (__nv_bfloat16*)x_hat_bf16;
   if (x_dtype == MH_F32)
     prologue_x_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
-                                                   inv_norm, xh, x_hat32, xnorm, t_raw, label_local);
+                                                   inv_norm, xh, x_hat32, xnorm, t_raw, label_local, strict_labels);
   else if (x_dtype == MH_BF16)
     prologue_x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, B_pad, labels, W, layout, C, ld,
-                                                           c_offset, inv_norm, xh, x_hat32, xnorm, t_raw, label_local);
+                                                           c_offset, inv_norm, xh, x_hat32, xnorm, t_raw, label_local, strict_labels);
   else if (x_dtype == MH_F16)
     prologue_x_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
-                                                    inv_norm, xh, x_hat32, xnorm, t_raw, label_local);
+                                                    inv_norm, xh, x_hat32, xnorm, t_raw, label_local, strict_labels);
   else
     MH_CHECK_ARG(false, "unknown x dtype");
   MH_LAUNCH_OK();
@@ -558,6 +560,7 @@ __global__ void __launch_bounds__(1024) row_params_kernel(MhParams p, int64_t B,
         norms = xc;
       } break;
     }
+    if (tr != tr) zt = tr;              // poisoned target cosine (label out of range): keep the NaN visible in the loss
     rowp[MH_RP_SCALE * ldp + i] = scale;
     rowp[MH_RP_THR * ldp + i] = thr;
     rowp[MH_RP_ZT * ldp + i] = zt;

@@ -149,7 +149,7 @@ class HeadEngine:
         label_local = self._buf("label_local", (B_pad,), torch.int32, dev)
         L.call("mh_prologue_x", _ptr(x), _DT[x.dtype], B, B_pad, _ptr(labels), _ptr(W), self.layout, Cn, ld,
                self.shard.c_offset, _ptr(inv_norm), _ptr(x_hat), _ptr(x_hat32), _ptr(xnorm), _ptr(t_raw),
-               _ptr(label_local), st)
+               _ptr(label_local), 1 if self.shard.world == 1 else 0, st)
         if self.shard.world > 1:
             # every rank needs every row's target cosine (thresholds, EMA); only the owner computed it
             self.shard.comm.allreduce_sum_(t_raw)

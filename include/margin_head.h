@@ -127,11 +127,12 @@ int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, void* w_hat
  * cosine gather (criterion.py:417,552).  labels are GLOBAL class ids (int64); this shard owns
  * [c_offset, c_offset + C).  Outputs: x_hat bf16 [B_pad,512] (rows >= B zeroed), x_hat32 fp32
  * [B,512], xnorm[B], t_raw[B] = <x_hat_i, w_hat_{y_i}> in fp32 (0 when the label is not owned),
- * label_local[B_pad] (int32; -1 when not owned or row >= B). */
+ * label_local[B_pad] (int32; -1 when not owned or row >= B).  strict_labels != 0 (unsharded head): a label outside
+ * [0, C) sets t_raw to NaN so that the loss is NaN (the reference's one_hot.scatter_ fails on such a label). */
 int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pad, const int64_t* labels,
                   const float* W, int layout, int64_t C, int64_t ld, int64_t c_offset,
                   const float* inv_norm, void* x_hat_bf16, float* x_hat32, float* xnorm, float* t_raw,
-                  int32_t* label_local, void* stream);
+                  int32_t* label_local, int strict_labels, void* stream);
 
 /* Per-row margin terms + batch-global state updates (CurricularFace EMA criterion.py:570-573,
  * AdaFace batch statistics criterion.py:876-885, MagFace loss_g criterion.py:1248).  margins may be

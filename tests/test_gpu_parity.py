@@ -200,6 +200,12 @@ def test_error_paths(pkg):
     with pytest.raises(ValueError):
         eh.fused_loss(torch.randn(4, 512, device="cuda"), torch.tensor([1, -1, 2, 3], device="cuda"))
     assert pkg._lib.load().mh_device_check() == 0
+    # a label outside [0, C) must not pass silently: the loss is NaN (the reference's scatter_ raises a device assert)
+    bad = torch.tensor([1, 2, 100, 3], device="cuda")
+    out = head.fused_loss(torch.randn(4, 512, device="cuda"), bad)
+    assert torch.isnan(out.loss)
+    out = head.fused_loss(torch.randn(4, 512, device="cuda"), torch.tensor([1, 2, 99, 3], device="cuda"))
+    assert torch.isfinite(out.loss)
 
 
 @pytest.mark.parametrize("B,Cn,fam", [(700, 20000, "arcface"), (19200, 600, "cosface"), (19200, 600, "mv_am")])

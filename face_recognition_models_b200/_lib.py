@@ -55,7 +55,7 @@ SIGNATURES = {
     "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i64, _vp],
-    "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, C.POINTER(C.c_int), _vp],
     "mh_vpl_mix": [_vp, _vp, _vp, C.c_float, _i64, _i64, _vp, _vp, _vp],
     "mh_pair_cosine": [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp],
     "mh_tc_fixref_ok": [_cfgp, _i64],
@@ -127,7 +127,7 @@ def _launches(name: str, args) -> int:
     if name == "mh_tc_backward_dx":
         return 0 if not getattr(args[4], "value", None) else 1
     if name == "mh_tc_backward_dx_stash":
-        return 0 if not getattr(args[7], "value", None) else 1
+        return 0 if not getattr(args[9], "value", None) else 1
     return 1
 
 

@@ -81,6 +81,8 @@ struct TcArgs {
   int rsum_parts;              // DW fused: number of partial planes of rsum (1 for the BWD_G sums)
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
+  int side_mv;                 // DX side pass, MV-Softmax: invert the hard-negative re-weighting u = a*c + b as well
+  float side_ha, side_hb;      //   (a, b) = (mv_weight, mv_weight - 1)
   const __nv_bfloat16* w_hat;  // DW fused
   const float* inv_norm;       // DW fused
   const float* gscal;          // DW fused
@@ -843,9 +845,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // sums are then reduced with shuffles -- no shared-memory traffic, no CTA barrier.  cos_ij is recovered from
           // the stash: E' = exp2(s2 cos - ref2)  =>  cos = log2(E') / s2 + ref2 / s2  (E' = 0: target / clamped / pad).
           const int ew = warp - EPI_WARP0;
-          float rh[4];
+          float rh[4], ucut[4];
+          // MV-Softmax: a stashed value is e * 1 with u = c (c <= thr_i) or e * a with u = a*c + b (c > thr_i).  Read as
+          // u_easy = log2(E')/s2 + kappa the two cases fall into disjoint ranges, (-inf, thr_i] and
+          // (a*thr_i + b + log2(a)/s2, +inf): ucut is the midpoint of the gap, so the branch is recovered exactly.
+          const float lg_ha = a.side_mv ? log2f(a.side_ha) : 0.f;
+          const float kappa_h = a.side_kappa - lg_ha * a.side_inv_s2, ha_inv = a.side_mv ? 1.f / a.side_ha : 1.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rh[j] = a.rho[w.m0 + lane + 32 * j];
+          for (int j = 0; j < 4; ++j) {
+            rh[j] = a.rho[w.m0 + lane + 32 * j];
+            const float thr = a.side_mv ? a.rowp[MH_RP_THR * a.ldp + w.m0 + lane + 32 * j] : 0.f;
+            ucut[j] = thr + 0.5f * ((a.side_ha - 1.f) * thr + a.side_hb + lg_ha * a.side_inv_s2);
+          }
           for (int kb = w.kb0; kb < w.kb1; ++kb) {
             mbar_wait(bar_empty + 8 * side_stage, side_phase);
             const uint32_t sa = tiles_base + side_stage * STAGE_BYTES;
@@ -868,8 +879,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float v0 = __uint_as_float(ww[e] << 16), v1 = __uint_as_float(ww[e] & 0xffff0000u);
-                const float c0 = fmaf(fmaxf(lg2(v0), -200.f), a.side_inv_s2, a.side_kappa);
-                const float c1 = fmaf(fmaxf(lg2(v1), -200.f), a.side_inv_s2, a.side_kappa);
+                const float l0 = fmaxf(lg2(v0), -200.f), l1 = fmaxf(lg2(v1), -200.f);
+                float c0 = fmaf(l0, a.side_inv_s2, a.side_kappa);
+                float c1 = fmaf(l1, a.side_inv_s2, a.side_kappa);
+                if (a.side_mv) {
+                  if (c0 > ucut[j]) c0 = (fmaf(l0, a.side_inv_s2, kappa_h) - a.side_hb) * ha_inv;
+                  if (c1 > ucut[j]) c1 = (fmaf(l1, a.side_inv_s2, kappa_h) - a.side_hb) * ha_inv;
+                }
                 acc8[2 * e] = fmaf(rh[j] * v0, c0, acc8[2 * e]);
                 acc8[2 * e + 1] = fmaf(rh[j] * v1, c1, acc8[2 * e + 1]);
               }
@@ -1058,8 +1074,8 @@ int variant_of(const MhParams& p) {
 template <int MODE>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
   const int v = variant_of(args.p);
-  if (MODE == MODE_FWDS && v != V_PLAIN && v != V_CLAMP) {
-    mh_set_error("the forward stash is only built for the plain / clamp families (see mh_tc_stash_ok)");
+  if (MODE == MODE_FWDS && v != V_PLAIN && v != V_CLAMP && v != V_MV) {
+    mh_set_error("the forward stash is not built for this family (see mh_tc_stash_ok)");
     return MH_ERR_ARG;
   }
   constexpr int M2 = MODE == MODE_FWDS ? MODE_FWD : MODE;       // never instantiated for FWDS (guarded above)
@@ -1067,7 +1083,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& a
     case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, st);
     case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, st);
     case V_SPHERE: return launch<M2, V_SPHERE>(ta, tb, args, st);
-    case V_MV: return launch<M2, V_MV>(ta, tb, args, st);
+    case V_MV: return launch<MODE, V_MV>(ta, tb, args, st);
     default: return launch<M2, V_CURR>(ta, tb, args, st);
   }
 }
@@ -1112,11 +1128,13 @@ extern "C" int mh_tc_fixref_ok(const mh_config* cfg_host, int64_t C) {
   return (p.s * MH_LOG2E * (family_umax(p) + 1.f) <= 200.f) ? 1 : 0;
 }
 
-// The forward stash additionally needs u = cos on every non-target column (no MV / Curricular re-weighting): the
-// backward recovers cos_ij from the stashed exponential for the projection term r_j.
+// The forward stash additionally needs cos_ij to be recoverable from the stashed exponential (the backward rebuilds the
+// projection term r_j from it): u = cos, or MV-Softmax's invertible u = w*cos + w - 1 on hard negatives.  CurricularFace's
+// cos*(t + cos) with its cos-dependent derivative is not.
 extern "C" int mh_tc_stash_ok(const mh_config* cfg_host, int64_t C) {
   if (!mh_tc_fixref_ok(cfg_host, C)) return 0;
-  return mh_make_params(cfg_host).hard_kind == 0 ? 1 : 0;
+  const MhParams p = mh_make_params(cfg_host);
+  return (p.hard_kind == 0 || (p.hard_kind == 1 && p.hard_a > 1.f)) ? 1 : 0;
 }
 
 // Test hook (host only, no device work): the (pair, m_tile, n_tile) triples of the A-stationary schedule in
@@ -1205,9 +1223,19 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
                                     lse2, nullptr, G_bf16, r_colsum, (cudaStream_t)stream);
 }
 
+// side pass of the stash backward (NULL rho = plain dx GEMM)
+struct DxSide {
+  const float* rho = nullptr;
+  float kappa = 0.f, inv_s2 = 0.f;
+  int mv = 0;
+  float ha = 1.f, hb = 0.f;
+  const float* rowp = nullptr;
+  int64_t ldp = 0;
+  float* rsum = nullptr;
+};
+
 static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
-                               int* n_split_host, const float* rho, float kappa, float inv_s2, float* r_colsum,
-                               void* stream) {
+                               int* n_split_host, const DxSide& side, void* stream) {
   MH_CHECK_ARG(B_pad > 0 && B_pad % BMT == 0 && C_pad > 0 && C_pad % BN == 0, "bad padded shape");
   const int m_tiles = (int)(B_pad / BMT);
   const int kb_total = (int)(C_pad / BK);
@@ -1227,25 +1255,30 @@ static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad,
   a.total_tiles = (int64_t)m_tiles * n_split;
   a.B_pad = B_pad; a.C_pad = C_pad; a.B = B_pad; a.C = C_pad;
   a.out = out; a.out_split_stride = B_pad * MH_D;
-  a.rho = rho; a.side_kappa = kappa; a.side_inv_s2 = inv_s2; a.rsum = r_colsum;
+  a.rho = side.rho; a.side_kappa = side.kappa; a.side_inv_s2 = side.inv_s2; a.rsum = side.rsum;
+  a.side_mv = side.mv; a.side_ha = side.ha; a.side_hb = side.hb; a.rowp = side.rowp; a.ldp = side.ldp;
   return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
                                  int* n_split_host, void* stream) {
-  return tc_backward_dx_impl(G_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, nullptr, 0.f, 0.f, nullptr, stream);
+  return tc_backward_dx_impl(G_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, DxSide{}, stream);
 }
 
 extern "C" int mh_tc_backward_dx_stash(const mh_config* cfg_host, const void* stash_bf16, int64_t B_pad, int64_t C,
-                                       int64_t C_pad, const void* w_hat_bf16, const float* rho, float* out,
-                                       float* r_colsum, int* n_split_host, void* stream) {
+                                       int64_t C_pad, const void* w_hat_bf16, const float* rho, const float* rowp,
+                                       int64_t ldp, float* out, float* r_colsum, int* n_split_host, void* stream) {
   MH_CHECK_ARG(cfg_host, "null pointer");
-  MH_CHECK_ARG(!out || (rho && r_colsum), "null pointer");
+  MH_CHECK_ARG(!out || (rho && r_colsum && rowp && ldp >= B_pad), "null pointer");
   MH_CHECK_ARG(mh_tc_stash_ok(cfg_host, C), "head not eligible for the stash backward (see mh_tc_stash_ok)");
   const MhParams p = mh_make_params(cfg_host);
   const float s2 = p.s * MH_LOG2E;
-  return tc_backward_dx_impl(stash_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, out ? rho : nullptr,
-                             (s2 * family_umax(p) - 102.f) / s2, 1.f / s2, r_colsum, stream);
+  DxSide side;
+  if (out) {
+    side.rho = rho; side.kappa = (s2 * family_umax(p) - 102.f) / s2; side.inv_s2 = 1.f / s2; side.rsum = r_colsum;
+    side.mv = (p.hard_kind == 1); side.ha = p.hard_a; side.hb = p.hard_b; side.rowp = rowp; side.ldp = ldp;
+  }
+  return tc_backward_dx_impl(stash_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, side, stream);
 }
 
 static int launch_dw(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_bf16, TcArgs& a,

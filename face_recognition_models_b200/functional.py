@@ -259,8 +259,8 @@ class HeadEngine:
             L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
                    _ptr(xs), _ptr(rho), _ptr(gty), st)
             part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
-            L.call("mh_tc_backward_dx_stash", C.byref(self.cfg), _ptr(G), B_pad, Cn, C_pad, _ptr(w_hat), _ptr(rho), _ptr(part),
-                   _ptr(rsum), C.byref(ns), st)
+            L.call("mh_tc_backward_dx_stash", C.byref(self.cfg), _ptr(G), B_pad, Cn, C_pad, _ptr(w_hat), _ptr(rho), _ptr(rowp),
+                   B_pad, _ptr(part), _ptr(rsum), C.byref(ns), st)
             if need_dx:
                 full = self._buf("dxhat_full", (1, B_pad, L.D), torch.float32, dev)
                 L.call("mh_stash_dx_combine", _ptr(part), n_split, split_stride, _ptr(rho), _ptr(gty), _ptr(label_local),

@@ -158,8 +158,8 @@ int64_t mh_tc_schedule_tiles(int units, int m_tiles, int n_tiles, int32_t* out, 
  * exp2(z*log2e - ref), ref = s*log2e*umax - 102, is a normal fp32/bf16 number, no running max is needed and the row
  * sums cannot overflow.  SphereFace (scale = |x|) and large s use the online-max forward. */
 int mh_tc_fixref_ok(const mh_config* cfg_host, int64_t C);
-/* 1 when the forward may stash for the backward: mh_tc_fixref_ok and no hard-negative re-weighting (MV-Softmax,
- * CurricularFace), because the backward recovers cos_ij from the stashed exponential.  Otherwise: recompute backward. */
+/* 1 when the forward may stash for the backward: mh_tc_fixref_ok and cos_ij recoverable from the stashed exponential
+ * (u = cos, or MV-Softmax's invertible u = w*cos + w - 1; not CurricularFace's cos*(t + cos)).  Otherwise: recompute. */
 int mh_tc_stash_ok(const mh_config* cfg_host, int64_t C);
 
 /* Fused cos-GEMM + margin + softmax statistics (replaces F.linear/torch.mm at criterion.py:65,176,267,
@@ -196,10 +196,11 @@ int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const vo
  * plain stores, every element written once: no atomics, bit-reproducible), with
  * cos_ij = log2(E'_ij)/(s log2e) + ref/(s log2e) recovered from the stash itself: the non-target part of the projection
  * term w^_j . dw^_j that mh_tc_backward_dw_fused needs, passed there with r_parts = B_pad/128 (the target column's part
- * is added by mh_stash_dw_target). */
+ * is added by mh_stash_dw_target).  MV-Softmax: hard negatives were stashed as w * exp2(.) with u = w*cos + w - 1; the two
+ * cases occupy disjoint ranges of log2(E') for a given row threshold (rowp plane MH_RP_THR), so cos is recovered exactly. */
 int mh_tc_backward_dx_stash(const mh_config* cfg_host, const void* stash_bf16, int64_t B_pad, int64_t C, int64_t C_pad,
-                            const void* w_hat_bf16, const float* rho, float* out, float* r_colsum, int* n_split_host,
-                            void* stream);
+                            const void* w_hat_bf16, const float* rho, const float* rowp, int64_t ldp, float* out,
+                            float* r_colsum, int* n_split_host, void* stream);
 
 /* dw_hat = G^T . x_hat, [C_pad, 512] fp32 (unscaled, unprojected). */
 int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,

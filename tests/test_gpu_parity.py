@@ -239,8 +239,8 @@ def test_stash_eligibility_and_override(pkg):
     cur = pkg.CurricularFace(512, 1000, m=0.5, s=64.0).cuda()                        # u can reach 2: 3*s*log2e > 200
     assert not cur._engine.stash_ok()
     mv = pkg.MV_Softmax(512, 1000, margin=0.35, mv_weight=1.12, s=32.0, margin_type="am").cuda()
-    assert not mv._engine.stash_ok()                                                 # hard negatives are re-weighted
-    assert lib.mh_tc_fixref_ok(ctypes_cfg(mv), 1000) == 1                            # ... but the forward still runs fixed-ref
+    assert mv._engine.stash_ok()                                                     # w*cos + w - 1 is invertible
+    assert lib.mh_tc_fixref_ok(ctypes_cfg(mv), 1000) == 1
     for h in (pkg.CosFace(512, 1000), pkg.AdaFace(512, 1000), pkg.MagFace(512, 1000), pkg.ElasticArcFace(512, 1000)):
         assert h.cuda()._engine.stash_ok()
     sph.backward_mode = "stash"

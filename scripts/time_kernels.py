@@ -41,8 +41,8 @@ def measure(tag):
 settings = [dict(kv.split("=") for kv in grp.split(",") if kv) for grp in os.environ.get("SETTINGS", "").split(";")]
 for rep in range(2):
     for st in settings:
-        for k in ("MH_DX_SIDE_DEBUG", "MH_EXP"):
-            os.environ.pop(k, None)
+        for k in [k for k in os.environ if k.startswith("MH_") and k not in ("MH_LIB",)]:
+            os.environ.pop(k, None)      # experiment toggles are per setting
         head.backward_mode = "auto"
         for k, v in st.items():
             if k == "MH_BACKWARD": head.backward_mode = v

@@ -6,6 +6,7 @@ Public API:
   FusedOutput         - result of ``head.fused_loss(feats, labels)``
   ShardedMarginHead   - class-sharded (Partial-FC style) head over torch.distributed / NCCL
   verification        - pair_cosine (CUDA) + the reference's LFW 10-fold protocol on embedding pairs
+  HeadSGD             - the reference's SGD(momentum, weight_decay) for the head parameter, fused with the next W prologue
 All compute runs in libmargin_head.so (hand-written sm_100a CUDA behind a C ABI, include/margin_head.h).
 """
 from .heads import (AdaFace, ArcFace, CosFace, CurricularFace, ElasticArcFace, ElasticCosFace, FusedOutput,
@@ -14,6 +15,8 @@ from .functional import HeadEngine, ShardInfo
 from .sharded import ShardedMarginHead, ShardComm, shard_range
 from . import _lib
 from . import verification
+from .optim import HeadSGD
 
 __all__ = ["AdaFace", "ArcFace", "CosFace", "CurricularFace", "ElasticArcFace", "ElasticCosFace", "FusedOutput",
-           "HEAD_CLASSES", "MagFace", "MV_Softmax", "SphereFace", "VPLArcFace", "HeadEngine", "ShardInfo", "ShardedMarginHead", "ShardComm", "shard_range", "_lib", "verification"]
+           "HEAD_CLASSES", "MagFace", "MV_Softmax", "SphereFace", "VPLArcFace", "HeadEngine", "ShardInfo", "ShardedMarginHead", "ShardComm", "shard_range", "_lib", "verification",
+           "HeadSGD"]

@@ -43,13 +43,14 @@ TILE = 128
 NTILE = 256
 D = 512
 
-_vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
 _cfgp = C.POINTER(MhConfig)
 
 # name -> argtypes; every function returns int (mh_status) unless listed in _RESTYPES
 SIGNATURES = {
     "mh_device_check": [],
     "mh_prologue_w": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp],
+    "mh_sgd_step_w": [_vp, _i32, _i64, _i64, _vp, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _i64, _vp, _vp],
     "mh_prologue_x": [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "mh_row_params": [_cfgp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],

@@ -5,12 +5,57 @@
 #include <cstdlib>
 
 // ------------------------------------------------------------------------------------------------
+// Optional fused optimizer: the reference trains the class centres with SGD(momentum 0.9, weight_decay 5e-4)
+// (model_utils.py:557).  The SGD variants of the kernels below apply that update to W while they stream it, so the
+// optimizer pass also leaves the next step's w^ / inv_norm behind and the next forward skips prologue_w.
+// Per element (torch.optim.SGD, dampening 0, no nesterov):  g' = g / scale + wd * w;  buf = momentum * buf + g';
+// w -= lr * buf.  A non-zero *found_inf (GradScaler) turns the update off; w^ is then rebuilt from the unchanged W.
+// ------------------------------------------------------------------------------------------------
+struct SgdArgs {
+  const float* grad;
+  float* mom;
+  float lr, momentum, wd;
+  const float* grad_scale;   // device scalar or null
+  const float* found_inf;    // device scalar or null
+};
+
+struct SgdCtx {
+  bool live;
+  float inv_scale;
+};
+
+__device__ __forceinline__ SgdCtx sgd_ctx(const SgdArgs& s) {
+  SgdCtx c;
+  c.live = s.found_inf == nullptr || __ldg(s.found_inf) == 0.f;
+  c.inv_scale = s.grad_scale ? 1.f / __ldg(s.grad_scale) : 1.f;
+  return c;
+}
+
+__device__ __forceinline__ float sgd_elem(float w, float g, float& m, const SgdArgs& s, const SgdCtx& c) {
+  const float gp = fmaf(s.wd, w, g * c.inv_scale);
+  m = __fadd_rn(__fmul_rn(m, s.momentum), gp);
+  return fmaf(-s.lr, m, w);
+}
+
+__device__ __forceinline__ float4 sgd_elem4(float4 w, float4 g, float4& m, const SgdArgs& s, const SgdCtx& c) {
+  float4 o;
+  o.x = sgd_elem(w.x, g.x, m.x, s, c);
+  o.y = sgd_elem(w.y, g.y, m.y, s, c);
+  o.z = sgd_elem(w.z, g.z, m.z, s, c);
+  o.w = sgd_elem(w.w, g.w, m.w, s, c);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
 // prologue_w, layout CD: W [C, 512] row-major. One warp per class; 16 B vector loads, 8 B bf16 stores.
 // Algorithmic bytes per class: 2048 read + 1024 bf16 write (+2048 optional fp32 copy) + 4.
+// SGD variant: + 4096 read (grad, momentum) + 4096 write (W, momentum).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prologue_w_cd_kernel(const float* __restrict__ W, int64_t C, int64_t ld,
+template <bool SGD>
+__global__ void __launch_bounds__(256) prologue_w_cd_kernel(float* __restrict__ W, int64_t C, int64_t ld,
                                                             __nv_bfloat16* __restrict__ what, int64_t C_pad,
-                                                            float* __restrict__ what32, float* __restrict__ inv_norm) {
+                                                            float* __restrict__ what32, float* __restrict__ inv_norm,
+                                                            SgdArgs sg) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= C_pad) return;
@@ -20,10 +65,29 @@ __global__ void __launch_bounds__(256) prologue_w_cd_kernel(const float* __restr
     for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = make_uint2(0u, 0u);
     return;
   }
-  const float4* src = reinterpret_cast<const float4*>(W + row * ld);
+  float4* src = reinterpret_cast<float4*>(W + row * ld);
   float4 v[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) v[k] = __ldg(src + lane + 32 * k);
+  for (int k = 0; k < 4; ++k) v[k] = SGD ? src[lane + 32 * k] : __ldg(src + lane + 32 * k);
+  if (SGD) {
+    const SgdCtx cx = sgd_ctx(sg);
+    if (cx.live) {
+      const float4* gsrc = reinterpret_cast<const float4*>(sg.grad + row * ld);
+      float4* msrc = reinterpret_cast<float4*>(sg.mom + row * ld);
+      float4 g[4], m[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g[k] = __ldg(gsrc + lane + 32 * k);
+        m[k] = msrc[lane + 32 * k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = sgd_elem4(v[k], g[k], m[k], sg, cx);
+        src[lane + 32 * k] = v[k];
+        msrc[lane + 32 * k] = m[k];
+      }
+    }
+  }
   float ss = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
@@ -48,9 +112,11 @@ __global__ void __launch_bounds__(256) prologue_w_cd_kernel(const float* __restr
 // normalised bf16 rows (coalesced along d). One read of W, one write of w_hat.
 // ------------------------------------------------------------------------------------------------
 #define PW_TC 32
-__global__ void __launch_bounds__(256) prologue_w_dc_kernel(const float* __restrict__ W, int64_t C, int64_t ld,
+template <bool SGD>
+__global__ void __launch_bounds__(256) prologue_w_dc_kernel(float* __restrict__ W, int64_t C, int64_t ld,
                                                             __nv_bfloat16* __restrict__ what, int64_t C_pad,
-                                                            float* __restrict__ what32, float* __restrict__ inv_norm) {
+                                                            float* __restrict__ what32, float* __restrict__ inv_norm,
+                                                            SgdArgs sg) {
   extern __shared__ float slab[];            // [512][33]
   __shared__ float part[8][PW_TC];
   __shared__ float invs[PW_TC];
@@ -59,17 +125,41 @@ __global__ void __launch_bounds__(256) prologue_w_dc_kernel(const float* __restr
   const int64_t c = c0 + tx;
   float ss = 0.f;
   // 16 independent 128-byte row loads in flight per warp (the loop was latency-bound at the compiler's unroll of 4:
-  // 2.6 TB/s; HBM needs ~40 KB in flight per SM)
+  // 2.6 TB/s; HBM needs ~40 KB in flight per SM); the SGD variant has 3 arrays to load, 8 rows of each per batch
+  constexpr int U = SGD ? 8 : 16;
+  SgdCtx cx;
+  if (SGD) cx = sgd_ctx(sg);
 #pragma unroll 1
-  for (int d0 = ty; d0 < MH_D; d0 += 8 * 16) {
-    float v[16];
+  for (int d0 = ty; d0 < MH_D; d0 += 8 * U) {
+    float v[U];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = (c < C) ? __ldg(W + (int64_t)(d0 + 8 * u) * ld + c) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      slab[(d0 + 8 * u) * 33 + tx] = v[u];
-      ss += v[u] * v[u];
+    for (int u = 0; u < U; ++u) {
+      const float* src = W + (int64_t)(d0 + 8 * u) * ld + c;
+      v[u] = (c < C) ? (SGD ? *src : __ldg(src)) : 0.f;
     }
+    if (SGD) {
+      if (cx.live && c < C) {
+        float g[U], m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t off = (int64_t)(d0 + 8 * u) * ld + c;
+          g[u] = __ldg(sg.grad + off);
+          m[u] = sg.mom[off];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t off = (int64_t)(d0 + 8 * u) * ld + c;
+          v[u] = sgd_elem(v[u], g[u], m[u], sg, cx);
+          W[off] = v[u];
+          sg.mom[off] = m[u];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) ss += v[u] * v[u];
+    const int skew = (ss < 0.f) ? 1 : 0;     // always 0; ties the stores to the whole batch of loads (see the dc4 kernel)
+#pragma unroll
+    for (int u = 0; u < U; ++u) slab[(d0 + 8 * u) * 33 + tx + skew] = v[u];
   }
   part[ty][tx] = ss;
   __syncthreads();
@@ -101,32 +191,65 @@ __global__ void __launch_bounds__(256) prologue_w_dc_kernel(const float* __restr
 
 // Same slab kernel for 16-byte-aligned rows (ld % 4 == 0, e.g. C = 2,000,000): one LDG.128 covers 4 d-rows x 32 classes
 // (8 lanes x 16 B per row), 8 of them in flight per warp = 4 KB, 96 KB per SM at 3 resident blocks.
-__global__ void __launch_bounds__(256) prologue_w_dc4_kernel(const float* __restrict__ W, int64_t C, int64_t ld,
+template <bool SGD>
+__global__ void __launch_bounds__(256) prologue_w_dc4_kernel(float* __restrict__ W, int64_t C, int64_t ld,
                                                              __nv_bfloat16* __restrict__ what, int64_t C_pad,
-                                                             float* __restrict__ what32, float* __restrict__ inv_norm) {
-  extern __shared__ float slab[];            // [512][33]
+                                                             float* __restrict__ what32, float* __restrict__ inv_norm,
+                                                             SgdArgs sg) {
+  // [512 d][8 chunks of 4 classes], 128 B per d-row; chunk q of row d sits at position q ^ ((d >> 1) & 7), which makes
+  // both the 16-byte stores of the load phase (8 lanes = 8 chunks of one row) and the 16-byte column reads of the write
+  // phase (8 lanes = one chunk of 8 row pairs) conflict-free.  (4-byte accesses into a [512][33] slab kept the
+  // shared-memory instruction queue full: mio_throttle was the top stall, 1.38 ms at C = 2M.)
+  extern __shared__ float4 slab4[];
   __shared__ float part[8][PW_TC];
-  __shared__ float invs[PW_TC];
+  __shared__ __align__(16) float invs[PW_TC];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int r4 = tx >> 3, q = tx & 7;        // row within the group of 4, float4 index within the 32-class row segment
   const int64_t c0 = (int64_t)blockIdx.x * PW_TC;
   const int64_t cq = c0 + 4 * q;
   float ss4[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int U = SGD ? 8 : 16;            // plain: all 16 row groups of the warp in flight at once (8 KB per warp)
+  SgdCtx cx;
+  if (SGD) cx = sgd_ctx(sg);
 #pragma unroll 1
-  for (int it0 = 0; it0 < 16; it0 += 16) {      // all 16 row groups of the warp in flight at once (8 KB per warp)
-    float4 v[16];
+  for (int it0 = 0; it0 < 16; it0 += U) {
+    float4 v[U];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int d = 4 * (ty + 8 * (it0 + u)) + r4;
       // C % 4 == 0, so a float4 is either entirely inside [0, C) or entirely outside
-      v[u] = (cq < C) ? __ldg(reinterpret_cast<const float4*>(W + (int64_t)d * ld + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* src = reinterpret_cast<const float4*>(W + (int64_t)d * ld + cq);
+      v[u] = (cq < C) ? (SGD ? *src : __ldg(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (SGD) {
+      if (cx.live && cq < C) {
+        float4 g[U], m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t off = (int64_t)(4 * (ty + 8 * (it0 + u)) + r4) * ld + cq;
+          g[u] = __ldg(reinterpret_cast<const float4*>(sg.grad + off));
+          m[u] = *reinterpret_cast<const float4*>(sg.mom + off);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t off = (int64_t)(4 * (ty + 8 * (it0 + u)) + r4) * ld + cq;
+          v[u] = sgd_elem4(v[u], g[u], m[u], sg, cx);
+          *reinterpret_cast<float4*>(W + off) = v[u];
+          *reinterpret_cast<float4*>(sg.mom + off) = m[u];
+        }
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int d = 4 * (ty + 8 * (it0 + u)) + r4;
-      float* dst = slab + d * 33 + 4 * q;
-      dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+    for (int u = 0; u < U; ++u) {
       ss4[0] += v[u].x * v[u].x; ss4[1] += v[u].y * v[u].y; ss4[2] += v[u].z * v[u].z; ss4[3] += v[u].w * v[u].w;
+    }
+    // ptxas otherwise sinks each load next to its shared-memory store (3 loads in flight instead of the whole batch):
+    // the store address below depends on the finished sums, i.e. on every load of the batch.  `skew` is always 0.
+    const int skew = (ss4[0] + ss4[1] + ss4[2] + ss4[3] < 0.f) ? 1 : 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int d = 4 * (ty + 8 * (it0 + u)) + r4;
+      slab4[d * 8 + (q ^ ((d >> 1) & 7)) + skew] = v[u];
     }
   }
   // sum over the 4 row groups of the warp (lane bits 3, 4), then over the 8 warps
@@ -150,16 +273,20 @@ __global__ void __launch_bounds__(256) prologue_w_dc4_kernel(const float* __rest
     if (c < C) inv_norm[c] = inv;
   }
   __syncthreads();
-  for (int r = ty; r < PW_TC; r += 8) {
-    const int64_t row = c0 + r;
-    if (row >= C_pad) continue;
-    const float inv = (row < C) ? invs[r] : 0.f;
-    // two consecutive d per lane: the column read of the [d][33] slab is 2-way bank-conflicted (4-way with four),
-    // and a warp still stores full 128-byte lines of bf16
+  // write phase: a lane takes 4 classes x 2 consecutive d (two 16-byte reads), a warp stores 128-byte lines of bf16
+  for (int it = ty; it < 64; it += 8) {
+    const int j = it & 7, k = it >> 3;         // class chunk, 64-wide d block
+    const int d = 64 * k + 2 * tx;
+    const int pos = j ^ ((d >> 1) & 7);
+    const float4 a = slab4[d * 8 + pos], b = slab4[(d + 1) * 8 + pos];
+    const float4 iv = *reinterpret_cast<const float4*>(invs + 4 * j);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, ivv[4] = {iv.x, iv.y, iv.z, iv.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int d = 2 * tx + 64 * k;
-      const float2 o = make_float2(slab[d * 33 + r] * inv, slab[(d + 1) * 33 + r] * inv);
+    for (int e = 0; e < 4; ++e) {
+      const int64_t row = c0 + 4 * j + e;
+      if (row >= C_pad) continue;
+      const float inv = (row < C) ? ivv[e] : 0.f;
+      const float2 o = make_float2(av[e] * inv, bv[e] * inv);
       *reinterpret_cast<__nv_bfloat162*>(what + row * MH_D + d) = __floats2bfloat162_rn(o.x, o.y);
       if (what32 && row < C) *reinterpret_cast<float2*>(what32 + row * MH_D + d) = o;
     }
@@ -173,30 +300,29 @@ __global__ void zero_pad_rows_kernel(__nv_bfloat16* what, int64_t row0, int64_t 
   if (i < n) what[row0 * MH_D + i] = __float2bfloat16(0.f);
 }
 
-extern "C" int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, void* w_hat_bf16, int64_t C_pad,
-                             float* w_hat32, float* inv_norm, void* stream) {
-  MH_CHECK_ARG(W && w_hat_bf16 && inv_norm, "null pointer");
-  MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % MH_TILE == 0, "C_pad must be a multiple of 128 and >= C");
-  MH_CHECK_ARG(((uintptr_t)W & 15) == 0 && ((uintptr_t)w_hat_bf16 & 15) == 0, "pointers must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
+template <bool SGD>
+static int launch_prologue_w(float* W, int layout, int64_t C, int64_t ld, void* w_hat_bf16, int64_t C_pad, float* w_hat32,
+                             float* inv_norm, const SgdArgs& sg, cudaStream_t st) {
   if (layout == MH_LAYOUT_CD) {
     MH_CHECK_ARG(ld >= MH_D && ld % 4 == 0, "CD layout needs ld >= 512 and ld % 4 == 0");
     dim3 grid((unsigned)((C_pad + 7) / 8));
-    prologue_w_cd_kernel<<<grid, 256, 0, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
+    prologue_w_cd_kernel<SGD><<<grid, 256, 0, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
   } else if (layout == MH_LAYOUT_DC) {
     MH_CHECK_ARG(ld >= C, "DC layout needs ld >= C");
     static bool attr_set = false;
     const int smem = MH_D * 33 * sizeof(float);
     if (!attr_set) {
-      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc_kernel<SGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc4_kernel<SGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set = true;
     }
     dim3 grid((unsigned)((C + PW_TC - 1) / PW_TC));
-    if (ld % 4 == 0 && C % 4 == 0 && ((uintptr_t)W & 15) == 0)
-      prologue_w_dc4_kernel<<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
+    bool vec4 = ld % 4 == 0 && C % 4 == 0 && ((uintptr_t)W & 15) == 0;
+    if (SGD) vec4 = vec4 && ((uintptr_t)sg.grad & 15) == 0 && ((uintptr_t)sg.mom & 15) == 0;
+    if (vec4)
+      prologue_w_dc4_kernel<SGD><<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
     else
-      prologue_w_dc_kernel<<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm);
+      prologue_w_dc_kernel<SGD><<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
     const int64_t covered = (int64_t)grid.x * PW_TC;
     if (covered < C_pad) {
       int64_t n = (C_pad - covered) * MH_D;
@@ -207,6 +333,29 @@ extern "C" int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, 
   }
   MH_LAUNCH_OK();
   return MH_OK;
+}
+
+extern "C" int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, void* w_hat_bf16, int64_t C_pad,
+                             float* w_hat32, float* inv_norm, void* stream) {
+  MH_CHECK_ARG(W && w_hat_bf16 && inv_norm, "null pointer");
+  MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % MH_TILE == 0, "C_pad must be a multiple of 128 and >= C");
+  MH_CHECK_ARG(((uintptr_t)W & 15) == 0 && ((uintptr_t)w_hat_bf16 & 15) == 0, "pointers must be 16-byte aligned");
+  SgdArgs none{};
+  return launch_prologue_w<false>(const_cast<float*>(W), layout, C, ld, w_hat_bf16, C_pad, w_hat32, inv_norm, none,
+                                  (cudaStream_t)stream);
+}
+
+extern "C" int mh_sgd_step_w(float* W, int layout, int64_t C, int64_t ld, const float* grad, float* momentum_buf, float lr,
+                             float momentum, float weight_decay, const float* grad_scale, const float* found_inf,
+                             void* w_hat_bf16, int64_t C_pad, float* inv_norm, void* stream) {
+  MH_CHECK_ARG(W && grad && momentum_buf && w_hat_bf16 && inv_norm, "null pointer");
+  MH_CHECK_ARG(C > 0 && C_pad >= C && C_pad % MH_TILE == 0, "C_pad must be a multiple of 128 and >= C");
+  MH_CHECK_ARG(((uintptr_t)W & 15) == 0 && ((uintptr_t)w_hat_bf16 & 15) == 0, "pointers must be 16-byte aligned");
+  if (layout == MH_LAYOUT_CD)
+    MH_CHECK_ARG(((uintptr_t)grad & 15) == 0 && ((uintptr_t)momentum_buf & 15) == 0, "pointers must be 16-byte aligned");
+  MH_CHECK_ARG(lr >= 0.f && momentum >= 0.f && weight_decay >= 0.f, "lr, momentum and weight_decay must be >= 0");
+  SgdArgs sg{grad, momentum_buf, lr, momentum, weight_decay, grad_scale, found_inf};
+  return launch_prologue_w<true>(W, layout, C, ld, w_hat_bf16, C_pad, nullptr, inv_norm, sg, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -79,6 +79,7 @@ class HeadEngine:
             setattr(self.cfg, k, v)
         self._ws: Dict[str, torch.Tensor] = {}
         self._gen = 0
+        self._shadow = None             # (W.data_ptr(), W._version, w_hat.data_ptr()) when sgd_step left a valid w_hat behind
         self.vpl = None                 # VPLArcFace: dict(mem, life, lamda) set by the head before each forward
         # "auto" | "stash" | "recompute"; MH_BACKWARD in the environment overrides (A/B measurements)
         self.backward_mode = os.environ.get("MH_BACKWARD", "auto")
@@ -104,6 +105,33 @@ class HeadEngine:
 
     def release_workspaces(self):
         self._ws.clear()
+        self._shadow = None
+
+    # -- fused optimizer step ---------------------------------------------------------------------
+    def sgd_step(self, W: torch.Tensor, grad: torch.Tensor, momentum_buf: torch.Tensor, lr: float, momentum: float,
+                 weight_decay: float, grad_scale: Optional[torch.Tensor] = None,
+                 found_inf: Optional[torch.Tensor] = None) -> None:
+        """SGD-momentum update of the class-centre parameter (model_utils.py:557, 186) in one pass that also writes the
+        next step's w_hat / inv_norm, so the next tensor-core forward of this head skips mh_prologue_w.  The shadow is
+        tied to W's storage and version counter: any other in-place write to W invalidates it."""
+        if not W.is_cuda:
+            raise L.MarginHeadError("margin head parameters must be CUDA tensors (no CPU fallback)")
+        assert W.dtype == torch.float32 and W.is_contiguous()
+        assert grad.dtype == torch.float32 and grad.is_contiguous() and grad.shape == W.shape, "grad must match W"
+        assert momentum_buf.dtype == torch.float32 and momentum_buf.is_contiguous() and momentum_buf.shape == W.shape
+        for t in (grad_scale, found_inf):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.numel() == 1)
+        dev = W.device
+        Cn = self.C
+        C_pad = _round_up(Cn, L.NTILE)
+        w_hat = self._buf("w_hat", (C_pad, L.D), torch.bfloat16, dev)
+        inv_norm = self._buf("inv_norm", (Cn,), torch.float32, dev)
+        self._gen += 1                  # a forward context that has not run its backward yet loses its w_hat
+        L.call("mh_sgd_step_w", _ptr(W), self.layout, Cn, W.shape[1], _ptr(grad), _ptr(momentum_buf), C.c_float(lr),
+               C.c_float(momentum), C.c_float(weight_decay), _ptr(grad_scale), _ptr(found_inf), _ptr(w_hat), C_pad,
+               _ptr(inv_norm), _stream())
+        torch.autograd.graph.increment_version(W)
+        self._shadow = (W.data_ptr(), W._version, w_hat.data_ptr())
 
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, state: torch.Tensor,
@@ -140,7 +168,10 @@ class HeadEngine:
         w_hat = self._buf("w_hat", (C_pad, L.D), torch.bfloat16, dev)
         inv_norm = self._buf("inv_norm", (Cn,), torch.float32, dev)
         w_hat32 = self._buf("w_hat32", (Cn, L.D), torch.float32, dev) if exact else None
-        L.call("mh_prologue_w", _ptr(W), self.layout, Cn, ld, _ptr(w_hat), C_pad, _ptr(w_hat32), _ptr(inv_norm), st)
+        if exact or self._shadow != (W.data_ptr(), W._version, w_hat.data_ptr()):
+            self._shadow = None
+            L.call("mh_prologue_w", _ptr(W), self.layout, Cn, ld, _ptr(w_hat), C_pad, _ptr(w_hat32), _ptr(inv_norm), st)
+        # else: sgd_step() wrote w_hat / inv_norm from this very W (same storage, same version counter)
 
         x_hat = self._buf("x_hat", (B_pad, L.D), torch.bfloat16, dev)
         x_hat32 = self._buf("x_hat32", (B, L.D), torch.float32, dev)

@@ -68,6 +68,13 @@ class _MarginHeadBase(nn.Module):
     def _param(self) -> torch.Tensor:
         return getattr(self, self.param_name)
 
+    # what optim.HeadSGD needs: the class-centre parameter and the engine whose workspace holds its w_hat
+    def head_parameter(self) -> torch.Tensor:
+        return self._param()
+
+    def head_engine(self):
+        return self._engine
+
     # hooks for heads with state ------------------------------------------------------------------
     def _push_state(self):
         pass

@@ -1,0 +1,69 @@
+"""SGD for the class-centre parameter of a margin head, fused with the next step's W prologue.
+
+The reference trains everything with one `optim.SGD(model.parameters(), lr, momentum=0.9, weight_decay=5e-4)`
+(main_code/utils/model_utils.py:557), stepped through `GradScaler.step` (model_utils.py:186).  For the head parameter
+that is a 20 B/element streaming pass over C x 512 floats, and the next forward then streams W again to normalise it.
+`HeadSGD` does both in one pass (`mh_sgd_step_w`): the update is torch.optim.SGD's (dampening 0, no nesterov), and
+the same kernel leaves the bf16 `w_hat` and `inv_norm` of the updated W in the head's workspace, so the next
+tensor-core forward skips `mh_prologue_w`.
+
+Use it next to the unchanged optimizer of the backbone:
+
+    opt_backbone = optim.SGD(model.backbone.parameters(), lr=lr, momentum=0.9, weight_decay=5e-4)
+    opt_head = HeadSGD([model.arcface], lr=lr, momentum=0.9, weight_decay=5e-4)
+    ...
+    scaler.step(opt_backbone); scaler.step(opt_head); scaler.update()
+
+It is a `torch.optim.Optimizer`: LR schedulers, `zero_grad`, `state_dict` (`momentum_buffer`, interchangeable with
+torch.optim.SGD's entry for the same parameter) and GradScaler (`grad_scale` / `found_inf` device scalars, no host
+sync, no separate unscale pass) work as usual.
+"""
+from typing import Iterable
+
+import torch
+
+from . import _lib as L
+
+
+class HeadSGD(torch.optim.Optimizer):
+    _step_supports_amp_scaling = True      # GradScaler hands over grad_scale / found_inf instead of unscaling first
+
+    def __init__(self, heads: Iterable[torch.nn.Module], lr: float, momentum: float = 0.9, weight_decay: float = 5e-4):
+        if lr < 0 or momentum < 0 or weight_decay < 0:
+            raise ValueError("lr, momentum and weight_decay must be >= 0")
+        heads = list(heads)
+        if not heads:
+            raise ValueError("HeadSGD needs at least one margin head")
+        self._engine_of = {}
+        params = []
+        for h in heads:
+            if not hasattr(h, "head_parameter") or not hasattr(h, "head_engine"):
+                raise TypeError(f"{type(h).__name__} is not a margin head of this package")
+            p = h.head_parameter()
+            self._engine_of[id(p)] = h
+            params.append(p)
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise L.MarginHeadError("HeadSGD runs on CUDA parameters only (no CPU fallback)")
+                g = p.grad
+                if g.is_sparse:
+                    raise L.MarginHeadError("HeadSGD does not take sparse gradients")
+                st = self.state[p]
+                if "momentum_buffer" not in st or st["momentum_buffer"] is None:
+                    st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                engine = self._engine_of[id(p)].head_engine()
+                engine.sgd_step(p, g.contiguous(), st["momentum_buffer"], float(group["lr"]), float(group["momentum"]),
+                                float(group["weight_decay"]), getattr(self, "grad_scale", None),
+                                getattr(self, "found_inf", None))      # set by GradScaler.step around this call
+        return loss

@@ -146,6 +146,12 @@ class ShardedMarginHead(nn.Module):
     def shard_parameter(self) -> torch.Tensor:
         return self.local._param()
 
+    def head_parameter(self) -> torch.Tensor:      # optim.HeadSGD protocol
+        return self.shard_parameter()
+
+    def head_engine(self) -> HeadEngine:
+        return self.engine
+
     def fused_loss(self, feats: torch.Tensor, labels: torch.Tensor) -> FusedOutput:
         self.local._check(feats, labels)
         self.local._pre_forward(feats)

@@ -123,6 +123,19 @@ int mh_device_check(void);
 int mh_prologue_w(const float* W, int layout, int64_t C, int64_t ld, void* w_hat_bf16, int64_t C_pad,
                   float* w_hat32, float* inv_norm, void* stream);
 
+/* Optimizer step of the class-centre parameter fused with the NEXT step's mh_prologue_w.
+ * Replaces optim.SGD(..., momentum=0.9, weight_decay=5e-4).step() on the head parameter (model_utils.py:557,
+ * applied at model_utils.py:186 through GradScaler.step) followed by the F.normalize of the next forward.
+ * In place, per element (torch.optim.SGD with dampening 0, no nesterov; momentum_buf starts at zero):
+ *   g' = grad / *grad_scale + weight_decay * w;  momentum_buf = momentum * momentum_buf + g';  w -= lr * momentum_buf
+ * and, from the updated W in the same pass, w_hat bf16 [C_pad, 512] and inv_norm[C] exactly as mh_prologue_w writes
+ * them.  grad and momentum_buf have W's layout and pitch.  grad_scale / found_inf are GradScaler's device scalars
+ * (NULL = no scaling / never skip); a non-zero *found_inf leaves W and momentum_buf untouched (w_hat is rebuilt from
+ * the unchanged W).  Algorithmic bytes per class: 3 x 2048 read + 2 x 2048 + 1024 + 4 written. */
+int mh_sgd_step_w(float* W, int layout, int64_t C, int64_t ld, const float* grad, float* momentum_buf, float lr,
+                  float momentum, float weight_decay, const float* grad_scale, const float* found_inf,
+                  void* w_hat_bf16, int64_t C_pad, float* inv_norm, void* stream);
+
 /* Replaces F.normalize(x) + torch.norm(x) (criterion.py:65,95,173,192,263,298,...) and the target
  * cosine gather (criterion.py:417,552).  labels are GLOBAL class ids (int64); this shard owns
  * [c_offset, c_offset + C).  Outputs: x_hat bf16 [B_pad,512] (rows >= B zeroed), x_hat32 fp32

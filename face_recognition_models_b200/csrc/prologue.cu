@@ -293,6 +293,102 @@ __global__ void __launch_bounds__(256) prologue_w_dc4_kernel(float* __restrict__
   }
 }
 
+// Plain prologue (no optimizer), 16-byte-aligned DC rows: persistent blocks, one per SM, stream 32-class tiles through a
+// 3-deep ring of swizzled slabs with cp.async, so two tiles (128 KB per SM) are always in flight while the block
+// reduces and writes the third.  (The one-tile-per-block kernel above alternates load / barrier / write phases with
+// 24 resident warps and stalls on long_scoreboard + barrier: 4.5 TB/s.)  Thread -> chunk mapping, summation order and
+// therefore every output bit are those of prologue_w_dc4_kernel.
+#define PW_NST 3
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) prologue_w_dc4p_kernel(const float* __restrict__ W, int64_t C, int64_t ld,
+                                                                 __nv_bfloat16* __restrict__ what, int64_t C_pad,
+                                                                 float* __restrict__ what32, float* __restrict__ inv_norm,
+                                                                 int64_t n_tiles) {
+  extern __shared__ float4 slab4[];            // PW_NST x [512 d][8 chunks], chunk q of row d at q ^ ((d >> 1) & 7)
+  __shared__ float part[8][PW_TC];
+  __shared__ __align__(16) float invs[PW_TC];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r4 = tx >> 3, q = tx & 7;
+  auto issue = [&](int64_t tile, int buf) {
+    const int64_t cq = tile * PW_TC + 4 * q;
+    const bool in = cq < C;                    // C % 4 == 0: a chunk is entirely inside or outside
+    const float* src = W + (in ? cq : 0);
+    float4* dst = slab4 + buf * (MH_D * 8);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int d = 4 * (ty + 8 * u) + r4;
+      cp_async16_zfill(dst + d * 8 + (q ^ ((d >> 1) & 7)), src + (int64_t)d * ld, in ? 16 : 0);
+    }
+  };
+  int64_t t = blockIdx.x;
+#pragma unroll
+  for (int s = 0; s < PW_NST - 1; ++s) {
+    if (t + (int64_t)s * gridDim.x < n_tiles) issue(t + (int64_t)s * gridDim.x, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int buf = 0;
+  for (; t < n_tiles; t += gridDim.x) {
+    const int64_t tn = t + (int64_t)(PW_NST - 1) * gridDim.x;
+    if (tn < n_tiles) issue(tn, (buf + PW_NST - 1) % PW_NST);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(PW_NST - 1) : "memory");
+    const float4* cur = slab4 + buf * (MH_D * 8);
+    const int64_t c0 = t * PW_TC;
+    float ss4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {             // the thread's own 16 chunks, in the order of the register kernel
+      const int d = 4 * (ty + 8 * u) + r4;
+      const float4 v = cur[d * 8 + (q ^ ((d >> 1) & 7))];
+      ss4[0] += v.x * v.x; ss4[1] += v.y * v.y; ss4[2] += v.z * v.z; ss4[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ss4[e] += __shfl_xor_sync(0xffffffffu, ss4[e], 8);
+      ss4[e] += __shfl_xor_sync(0xffffffffu, ss4[e], 16);
+    }
+    if (r4 == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) part[ty][4 * q + e] = ss4[e];
+    }
+    __syncthreads();                           // every thread has waited for its own copies: the slab is complete
+    if (ty == 0) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += part[k][tx];
+      const float inv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+      invs[tx] = inv;
+      if (c0 + tx < C) inv_norm[c0 + tx] = inv;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int it = ty; it < 64; it += 8) {
+      const int j = it & 7, k = it >> 3;       // class chunk (4 classes, all inside or all outside [0, C)), 64-wide d block
+      const int d = 64 * k + 2 * tx;
+      const int pos = j ^ ((d >> 1) & 7);
+      const float4 a = cur[d * 8 + pos], b = cur[(d + 1) * 8 + pos];
+      const int64_t row0 = c0 + 4 * j;
+      if (row0 >= C_pad) continue;
+      const bool in = row0 < C;
+      float4 iv = *reinterpret_cast<const float4*>(invs + 4 * j);
+      if (!in) iv = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, ivv[4] = {iv.x, iv.y, iv.z, iv.w};
+      __nv_bfloat16* dst = what + row0 * MH_D + d;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 o = make_float2(av[e] * ivv[e], bv[e] * ivv[e]);
+        *reinterpret_cast<__nv_bfloat162*>(dst + e * MH_D) = __floats2bfloat162_rn(o.x, o.y);
+        if (what32 && in) *reinterpret_cast<float2*>(what32 + (row0 + e) * MH_D + d) = o;
+      }
+    }
+    __syncthreads();                           // the slab, part[] and invs[] are reused from here on
+    buf = (buf + 1) % PW_NST;
+  }
+}
+
 // zero the padding rows [C, C_pad) that no DC block covers
 __global__ void zero_pad_rows_kernel(__nv_bfloat16* what, int64_t row0, int64_t row1) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,7 +415,19 @@ static int launch_prologue_w(float* W, int layout, int64_t C, int64_t ld, void* 
     dim3 grid((unsigned)((C + PW_TC - 1) / PW_TC));
     bool vec4 = ld % 4 == 0 && C % 4 == 0 && ((uintptr_t)W & 15) == 0;
     if (SGD) vec4 = vec4 && ((uintptr_t)sg.grad & 15) == 0 && ((uintptr_t)sg.mom & 15) == 0;
-    if (vec4)
+    if (vec4 && !SGD) {
+      static int n_sm = 0;
+      const int smem_p = PW_NST * MH_D * 8 * (int)sizeof(float4);
+      if (!n_sm) {
+        int dev = 0;
+        MH_CUDA_OK(cudaGetDevice(&dev));
+        MH_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc4p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+      }
+      const int64_t n_tiles = grid.x;
+      const unsigned nb = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
+      prologue_w_dc4p_kernel<<<nb, 256, smem_p, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, n_tiles);
+    } else if (vec4)
       prologue_w_dc4_kernel<SGD><<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
     else
       prologue_w_dc_kernel<SGD><<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);

@@ -50,11 +50,12 @@ def main():
     if world > 1:
         backbone = nn.parallel.DistributedDataParallel(backbone, device_ids=[local])
         head = pkg.ShardedMarginHead("arcface", a.classes, s=64.0, m=0.5, easy_margin=False, dx_scale=world).to(dev)
-        head_params = [head.shard_parameter()]
     else:
         head = pkg.ArcFace(512, a.classes, s=64.0, m=0.5, easy_margin=False).to(dev)
-        head_params = list(head.parameters())
-    opt = torch.optim.SGD(list(backbone.parameters()) + head_params, lr=a.lr, momentum=0.9, weight_decay=5e-4)
+    # model_utils.py:557 builds one SGD over everything; here the head parameter goes to HeadSGD (same update, fused
+    # with the next step's W prologue), the backbone keeps torch.optim.SGD
+    opt = torch.optim.SGD(backbone.parameters(), lr=a.lr, momentum=0.9, weight_decay=5e-4)
+    opt_head = pkg.HeadSGD([head], lr=a.lr, momentum=0.9, weight_decay=5e-4)
     # model_utils.py:559 uses the default GradScaler (init_scale 65536): with fp16 features its first steps overflow and
     # are skipped while the scale halves; start lower so that a short demo run shows the loss moving
     scaler = torch.amp.GradScaler("cuda", init_scale=a.init_scale)
@@ -67,8 +68,10 @@ def main():
         out = head.fused_loss(feats, target)
         loss = out.loss + a.lambda_g * out.loss_g
         opt.zero_grad(set_to_none=True)
+        opt_head.zero_grad(set_to_none=True)
         scaler.scale(loss).backward()
         scaler.step(opt)
+        scaler.step(opt_head)
         scaler.update()
         lv = loss.item()
         if rank == 0:

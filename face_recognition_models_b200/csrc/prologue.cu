@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) prologue_w_dc4_kernel(float* __restrict__
 // Plain prologue (no optimizer), 16-byte-aligned DC rows: persistent blocks, one per SM, stream 32-class tiles through a
 // 3-deep ring of swizzled slabs with cp.async, so two tiles (128 KB per SM) are always in flight while the block
 // reduces and writes the third.  (The one-tile-per-block kernel above alternates load / barrier / write phases with
-// 24 resident warps and stalls on long_scoreboard + barrier: 4.5 TB/s.)  Thread -> chunk mapping, summation order and
+// 24 resident warps and stalls on long_scoreboard + barrier: 4.5 TB/s at C = 2M; this one 5.1-5.6 TB/s.)  Thread -> chunk mapping, summation order and
 // therefore every output bit are those of prologue_w_dc4_kernel.
 #define PW_NST 3
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {

@@ -107,6 +107,11 @@ class HeadEngine:
         self._ws.clear()
         self._shadow = None
 
+    def invalidate_shadow(self):
+        """Forget the w_hat left by sgd_step().  Only needed after writing the parameter behind autograd's back
+        (`W.data.<op>_()`, raw pointers): such writes do not move W's version counter."""
+        self._shadow = None
+
     # -- fused optimizer step ---------------------------------------------------------------------
     def sgd_step(self, W: torch.Tensor, grad: torch.Tensor, momentum_buf: torch.Tensor, lr: float, momentum: float,
                  weight_decay: float, grad_scale: Optional[torch.Tensor] = None,

@@ -14,6 +14,11 @@ Use it next to the unchanged optimizer of the backbone:
     ...
     scaler.step(opt_backbone); scaler.step(opt_head); scaler.update()
 
+The shadow is keyed on the parameter's storage and autograd version counter, so `load_state_dict`, `W.copy_()`,
+`W.mul_()` ... under `torch.no_grad()` drop it automatically; a write through `W.data` does not move the counter -
+call `head.head_engine().invalidate_shadow()` after one.  `lr` is passed to the kernel by value (a CUDA-graph capture
+of `step()` freezes it).
+
 It is a `torch.optim.Optimizer`: LR schedulers, `zero_grad`, `state_dict` (`momentum_buffer`, interchangeable with
 torch.optim.SGD's entry for the same parameter) and GradScaler (`grad_scale` / `found_inf` device scalars, no host
 sync, no separate unscale pass) work as usual.

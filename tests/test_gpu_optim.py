@@ -100,13 +100,19 @@ def test_shadow_is_dropped_when_w_changes_elsewhere():
     with torch.no_grad():
         head.weight.mul_(0.5)                   # any other in-place write bumps the version counter
     assert "mh_prologue_w" in _called(lambda: head.fused_loss(x, y))
-    # ... and a prologue run by a different parameter tensor on the same engine drops it too
     opt.zero_grad()
     head.fused_loss(x, y).loss.backward()
     opt.step()
     head.mode = "exact"                         # the exact path needs the fp32 w_hat: prologue, shadow dropped
     assert "mh_prologue_w" in _called(lambda: head.fused_loss(x, y))
     head.mode = "tc"
+    assert "mh_prologue_w" in _called(lambda: head.fused_loss(x, y))
+    # a write through .data is invisible to the version counter: the documented escape hatch
+    opt.zero_grad()
+    head.fused_loss(x, y).loss.backward()
+    opt.step()
+    head.weight.data.mul_(2.0)
+    head.head_engine().invalidate_shadow()
     assert "mh_prologue_w" in _called(lambda: head.fused_loss(x, y))
 
 

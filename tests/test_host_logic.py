@@ -82,3 +82,36 @@ def test_constructor_signatures_equal_reference():
         rp = [(p.name, p.default) for p in ref.parameters.values()]
         gp = [(p.name, p.default) for p in got.parameters.values()]
         assert rp == gp, (name, rp, gp)
+
+
+def test_head_sgd_host_side():
+    """HeadSGD is a torch.optim.Optimizer over the heads' class-centre parameters; it refuses foreign modules and CPU
+    parameters (the update is CUDA-only: no fallback), and its param_groups drive LR schedulers as usual."""
+    import torch
+    import face_recognition_models_b200 as pkg
+    from face_recognition_models_b200 import _lib as L
+    a, b = pkg.ArcFace(512, 32), pkg.CosFace(512, 48)
+    opt = pkg.HeadSGD([a, b], lr=0.1, momentum=0.9, weight_decay=5e-4)
+    assert isinstance(opt, torch.optim.Optimizer) and opt._step_supports_amp_scaling
+    assert [p.shape for p in opt.param_groups[0]["params"]] == [a.weight.shape, b.kernel.shape]
+    assert a.head_parameter() is a.weight and b.head_parameter() is b.kernel
+    assert a.head_engine() is a._engine
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
+    opt.step()                                   # no grads yet: nothing to do, must not touch the library
+    sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 0.05) < 1e-12
+    a.weight.grad = torch.zeros_like(a.weight)
+    with pytest.raises(L.MarginHeadError):
+        opt.step()
+    with pytest.raises(TypeError):
+        pkg.HeadSGD([torch.nn.Linear(4, 4)], lr=0.1)
+    with pytest.raises(ValueError):
+        pkg.HeadSGD([], lr=0.1)
+    with pytest.raises(ValueError):
+        pkg.HeadSGD([a], lr=-1.0)
+    # the shadow bookkeeping is plain host state
+    eng = a.head_engine()
+    assert eng._shadow is None
+    eng._shadow = (1, 2, 3)
+    eng.invalidate_shadow()
+    assert eng._shadow is None

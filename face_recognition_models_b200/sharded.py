@@ -87,6 +87,7 @@ class _ShardedFusedLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_local, W_local, labels_local, head, margins_local, grad_enabled=True):
         comm: ShardComm = head.comm
+        head.engine.prefetch_w(W_local)              # the GPU normalises the shard while the host issues the gathers
         x_g = comm.gather_rows(x_local.contiguous())
         y_g = comm.gather_rows(labels_local.contiguous().to(torch.int64))
         margins_g = comm.gather_rows(margins_local.contiguous()) if margins_local is not None else None

@@ -88,11 +88,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("MH_LIB") or LIB_PATH      # MH_LIB: an experimental build (scripts/build_variant.sh)
+    if not os.path.exists(path):
         raise MarginHeadError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the margin head.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -27,6 +27,20 @@ extern "C" int mh_device_check(void) {
   return MH_OK;
 }
 
+int mh_num_sms() {
+  static MhDeviceOnce once;
+  static int n_sm[MH_MAX_DEVICES];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MH_MAX_DEVICES) return 148;
+  mh_once_per_device(once, [&] {
+    int n = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    n_sm[dev] = (e == cudaSuccess && n > 0) ? n : 148;
+    return cudaSuccess;
+  });
+  return n_sm[dev];
+}
+
 // Expand the reference constructor arguments into the constants every kernel needs.
 // ArcFace criterion.py:246-249, CurricularFace :507-510, MV_Softmax :371-374; clamps per family.
 MhParams mh_make_params(const mh_config* c) {

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
+#include <mutex>
 #include "../../include/margin_head.h"
 
 #define MH_LOG2E 1.4426950408889634f
@@ -37,6 +38,26 @@ void mh_set_error(const char* fmt, ...);
       return MH_ERR_CUDA;                                                           \
     }                                                                               \
   } while (0)
+
+// Per-device one-time host state (kernel attributes are per device; so is the SM count): one once-flag per device
+// ordinal, so the entry points stay re-entrant and a process may drive several GPUs ("no globals
+// except immutable kernel attributes set once under std::call_once").
+constexpr int MH_MAX_DEVICES = 64;
+struct MhDeviceOnce {
+  std::once_flag flag[MH_MAX_DEVICES];
+  cudaError_t err[MH_MAX_DEVICES];
+};
+template <class Fn>
+inline cudaError_t mh_once_per_device(MhDeviceOnce& o, Fn&& fn) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= MH_MAX_DEVICES) return fn();          // beyond the cache: set it every time (cheap)
+  std::call_once(o.flag[dev], [&] { o.err[dev] = fn(); });
+  return o.err[dev];
+}
+// SM count of the CURRENT device (cached per device ordinal; 148 if the query fails).
+int mh_num_sms();
 
 // Device copy of the hyper-parameters + derived constants, passed by value to kernels.
 struct MhParams {

@@ -514,12 +514,11 @@ extern "C" int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, c
     norm_backward_w_cd_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(dw_hat, (const __nv_bfloat16*)w_hat_bf16, w_hat32,
                                                                       inv_norm, gscal, class_scale, C, dW, ld);
   } else if (layout == MH_LAYOUT_DC) {
-    static bool attr_set = false;
+    static MhDeviceOnce attr_once;
     const int smem = MH_D * 33 * sizeof(float);
-    if (!attr_set) {
-      MH_CUDA_OK(cudaFuncSetAttribute(norm_backward_w_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
+    MH_CUDA_OK(mh_once_per_device(attr_once, [&] {
+      return cudaFuncSetAttribute(norm_backward_w_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }));
     norm_backward_w_dc_kernel<<<(unsigned)((C + 31) / 32), 256, smem, st>>>(dw_hat, (const __nv_bfloat16*)w_hat_bf16,
                                                                           w_hat32, inv_norm, gscal, class_scale, C, dW, ld);
   } else {

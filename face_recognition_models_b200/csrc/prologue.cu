@@ -405,25 +405,20 @@ static int launch_prologue_w(float* W, int layout, int64_t C, int64_t ld, void* 
     prologue_w_cd_kernel<SGD><<<grid, 256, 0, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
   } else if (layout == MH_LAYOUT_DC) {
     MH_CHECK_ARG(ld >= C, "DC layout needs ld >= C");
-    static bool attr_set = false;
+    static MhDeviceOnce attr_once;
     const int smem = MH_D * 33 * sizeof(float);
-    if (!attr_set) {
-      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc_kernel<SGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc4_kernel<SGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
+    const int smem_p = PW_NST * MH_D * 8 * (int)sizeof(float4);
+    MH_CUDA_OK(mh_once_per_device(attr_once, [&] {
+      cudaError_t e = cudaFuncSetAttribute(prologue_w_dc_kernel<SGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(prologue_w_dc4_kernel<SGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(prologue_w_dc4p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+      return e;
+    }));
     dim3 grid((unsigned)((C + PW_TC - 1) / PW_TC));
     bool vec4 = ld % 4 == 0 && C % 4 == 0 && ((uintptr_t)W & 15) == 0;
     if (SGD) vec4 = vec4 && ((uintptr_t)sg.grad & 15) == 0 && ((uintptr_t)sg.mom & 15) == 0;
     if (vec4 && !SGD) {
-      static int n_sm = 0;
-      const int smem_p = PW_NST * MH_D * 8 * (int)sizeof(float4);
-      if (!n_sm) {
-        int dev = 0;
-        MH_CUDA_OK(cudaGetDevice(&dev));
-        MH_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        MH_CUDA_OK(cudaFuncSetAttribute(prologue_w_dc4p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
-      }
+      const int n_sm = mh_num_sms();
       const int64_t n_tiles = grid.x;
       const unsigned nb = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
       prologue_w_dc4p_kernel<<<nb, 256, smem_p, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, n_tiles);

@@ -1025,25 +1025,15 @@ int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, in
   return MH_OK;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return mh_num_sms(); }     // per device (capi.cu)
 
 template <int MODE, int V>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
-  static bool attr_set = false;
+  static MhDeviceOnce attr_once;               // one per template instance; kernel attributes are per device
   constexpr int smem = mode_smem_bytes(MODE);
-  if (!attr_set) {
-    MH_CUDA_OK(cudaFuncSetAttribute(tc_kernel<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  MH_CUDA_OK(mh_once_per_device(attr_once, [&] {
+    return cudaFuncSetAttribute(tc_kernel<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  }));
   const int units = num_sms() / 2;
   // A-stationary kernels use a static schedule over exactly `units` pairs (pairs without work exit at once)
   const int n = mode_astat(MODE) ? units : (int)std::min<int64_t>(args.total_tiles, units);
@@ -1255,7 +1245,8 @@ static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad,
     const double cost = (double)waves * (per_n + 8);
     if (cost < best * 0.97) { best = cost; n_split = n_eff; }
   }
-  if (const char* e = getenv("MH_DX_SPLIT")) n_split = std::max(1, std::min(atoi(e), kb_total));   // experiments
+  static const int env_split = [] { const char* e = getenv("MH_DX_SPLIT"); return e ? atoi(e) : 0; }();   // experiments; read once
+  if (env_split > 0) n_split = std::max(1, std::min(env_split, kb_total));
   int per = (kb_total + n_split - 1) / n_split;
   n_split = (kb_total + per - 1) / per;                 // no empty splits
   if (n_split_host) *n_split_host = n_split;

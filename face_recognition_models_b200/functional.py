@@ -18,6 +18,7 @@ The sequence mirrors the reference forward (criterion.py, any head) + ``nn.Cross
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 import os
 from dataclasses import dataclass
@@ -34,6 +35,30 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device_of(argpos: int, same_device=(0, 1, 2, 3)):
+    """Run the method with the device of its ``argpos``-th positional tensor as the current CUDA device, so the stream
+    handed to the C ABI, the workspaces and every launch belong to the GPU that holds the data (a head on cuda:1 works
+    while cuda:0 is current, as the reference's modules do).  The tensor arguments at positions ``same_device`` (x / W /
+    labels / state, or W / grad / momentum) must live on that device."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(self, *args, **kw):
+            t = args[argpos]
+            if isinstance(t, dict):
+                t = t["x_hat"]
+            if not t.is_cuda:
+                raise L.MarginHeadError("margin head tensors must be CUDA tensors (no CPU fallback)")
+            for a in [args[i] for i in same_device if i < len(args)]:
+                if isinstance(a, torch.Tensor) and a.device != t.device:
+                    raise L.MarginHeadError(f"margin head tensors must share one device: {a.device} vs {t.device}")
+            if torch.cuda.current_device() == t.device.index:
+                return fn(self, *args, **kw)
+            with torch.cuda.device(t.device):
+                return fn(self, *args, **kw)
+        return wrapped
+    return deco
 
 
 def _round_up(a: int, b: int) -> int:
@@ -114,6 +139,7 @@ class HeadEngine:
         self._shadow = None
 
     # -- fused optimizer step ---------------------------------------------------------------------
+    @_on_device_of(0)
     def sgd_step(self, W: torch.Tensor, grad: torch.Tensor, momentum_buf: torch.Tensor, lr: float, momentum: float,
                  weight_decay: float, grad_scale: Optional[torch.Tensor] = None,
                  found_inf: Optional[torch.Tensor] = None) -> None:
@@ -140,11 +166,12 @@ class HeadEngine:
         self._shadow = (W.data_ptr(), W._version, w_hat.data_ptr())
         self._shadow_once = False
 
+    @_on_device_of(0)
     def prefetch_w(self, W: torch.Tensor) -> None:
         """Launch the W prologue ahead of the rest of the forward: it does not depend on the batch, so the sharded head
         calls this before its all-gathers and the GPU has 0.1-0.9 ms of work while the host issues the collectives.
         forward() then finds w_hat valid for this W (same mechanism as the shadow left by sgd_step)."""
-        if self.mode == "exact" or not W.is_cuda or W.dtype != torch.float32 or not W.is_contiguous():
+        if self.mode == "exact" or W.dtype != torch.float32 or not W.is_contiguous():
             return
         dev = W.device
         Cn = self.C
@@ -158,6 +185,7 @@ class HeadEngine:
         self._shadow_once = True
 
     # -- forward ----------------------------------------------------------------------------------
+    @_on_device_of(0)
     def forward(self, x: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, state: torch.Tensor,
                 margins: Optional[torch.Tensor], update_state: bool = True, want_dense: bool = False,
                 want_grad: bool = False):
@@ -280,6 +308,7 @@ class HeadEngine:
                     W_shape=tuple(W.shape), ld=ld, stash=stash, w_gemm=w_gemm, vpl_alpha=alpha)
 
     # -- backward of the fused loss ------------------------------------------------------------------
+    @_on_device_of(0)
     def backward(self, ctx: Dict, g_loss: torch.Tensor, g_lossg: Optional[torch.Tensor],
                  need_dx: bool = True, need_dw: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
         """Returns (dxhat_partials_or_dx, dW).  For world == 1 the first element is dx [B,512] in x's dtype."""
@@ -435,6 +464,7 @@ class HeadEngine:
         return dx, dW
 
     # -- backward of the compat (materialised logits) outputs ---------------------------------------
+    @_on_device_of(0)
     def backward_dense(self, ctx: Dict, dlogits: Optional[torch.Tensor], dpre: Optional[torch.Tensor],
                        g_lossg: Optional[torch.Tensor], need_dx=True, need_dw=True):
         if ctx["gen"] != self._gen:
@@ -497,7 +527,6 @@ class DenseMarginLogitsFn(torch.autograd.Function):
     def backward(ctx, dpre, dlogits, _gn, g_lossg):
         eng = ctx.engine
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if dpre is not None and not bool(torch.count_nonzero(dpre)):
-            dpre = None
+        # an all-zero dpre (the caller only differentiated `logits`) is handled by the kernel: no host sync here
         dx, dW = eng.backward_dense(ctx.c, dlogits, dpre, g_lossg, need_dx, need_dw)
         return dx, dW, None, None, None, None, None

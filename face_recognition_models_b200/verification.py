@@ -26,6 +26,13 @@ def pair_cosine(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
         raise L.MarginHeadError("pair_cosine inputs must be CUDA tensors (no CPU fallback)")
     if e1.dim() != 2 or e1.shape != e2.shape or e1.dtype != e2.dtype or e1.dtype not in _DT:
         raise ValueError("pair_cosine expects two [N, d] tensors of the same shape and dtype (fp32 / bf16 / fp16)")
+    if e1.device != e2.device:
+        raise L.MarginHeadError(f"pair_cosine inputs must share one device: {e1.device} vs {e2.device}")
+    with torch.cuda.device(e1.device):               # launch on the GPU that holds the data, whatever is current
+        return _pair_cosine(e1, e2)
+
+
+def _pair_cosine(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
     L.check(L.load().mh_device_check(), "mh_device_check")
     if e1.stride(1) != 1:
         e1 = e1.contiguous()

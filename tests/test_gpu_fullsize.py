@@ -15,57 +15,9 @@ CHUNK = 125_000
 
 
 def _fp32_chunked_reference(x, W, y, family="arcface", m=M):
-    """loss, dx, dW of ArcFace(easy_margin=False) (criterion.py:262-300) or CosFace (criterion.py:161-195; W is the
-    class-major view of its [D, C] kernel) + mean cross-entropy; fp32 GEMMs (TF32 off), fp64 softmax statistics."""
-    assert not torch.backends.cuda.matmul.allow_tf32
-    cos_m, sin_m = math.cos(m), math.sin(m)
-    th, mm = math.cos(math.pi - m), math.sin(math.pi - m) * m
-    xn = x.norm(dim=1, keepdim=True)
-    xh = x / xn.clamp_min(1e-12)
-    inv_w = 1.0 / W.norm(dim=1).clamp_min(1e-12)                       # [C]
-    wy = W[y] * inv_w[y, None]
-    t = (xh * wy).sum(1)                                                # target cosine
-    if family == "arcface":
-        sine = torch.sqrt((1.0 - t * t).clamp(0, 1))
-        hard = t > th
-        phi = torch.where(hard, t * cos_m - sine * sin_m, t - mm)
-        dphi = torch.where(hard, cos_m + sin_m * t / sine.clamp_min(1e-12), torch.ones_like(t))
-    else:
-        phi = t - m                                                     # |cos| < 1 here: the reference's clamp is inactive
-        dphi = torch.ones_like(t)
-    zt = S * phi
-    rows = torch.arange(B, device=x.device)
-    # pass 1: log-sum-exp over all classes with the target column replaced by the margin logit
-    mx = torch.full((B,), -float("inf"), dtype=torch.float64, device=x.device)
-    sm = torch.zeros(B, dtype=torch.float64, device=x.device)
-    for c0 in range(0, CN, CHUNK):
-        c1 = min(CN, c0 + CHUNK)
-        Sc = (xh @ (W[c0:c1] * inv_w[c0:c1, None]).t()) * S
-        own = (y >= c0) & (y < c1)
-        Sc[rows[own], y[own] - c0] = zt[own]
-        Sd = Sc.double()
-        m_new = torch.maximum(mx, Sd.max(1).values)
-        sm = sm * torch.exp(mx - m_new) + torch.exp(Sd - m_new[:, None]).sum(1)
-        mx = m_new
-    lse = mx + torch.log(sm)
-    loss = (lse - zt.double()).mean()
-    # pass 2: gradients
-    dxh = torch.zeros(B, D, dtype=torch.float32, device=x.device)
-    dW = torch.empty_like(W)
-    for c0 in range(0, CN, CHUNK):
-        c1 = min(CN, c0 + CHUNK)
-        wh = W[c0:c1] * inv_w[c0:c1, None]
-        Sc = (xh @ wh.t()) * S
-        own = (y >= c0) & (y < c1)
-        Sc[rows[own], y[own] - c0] = zt[own]
-        P = torch.exp(Sc.double() - lse[:, None]).float()
-        G = P * (S / B)                                                  # dL/dcos_ij off the target
-        G[rows[own], y[own] - c0] = (P[rows[own], y[own] - c0] - 1.0) * (S / B) * dphi[own]
-        dxh += G @ wh
-        dwh = G.t() @ xh
-        dW[c0:c1] = (dwh - wh * (wh * dwh).sum(1, keepdim=True)) * inv_w[c0:c1, None]
-    dx = (dxh - xh * (xh * dxh).sum(1, keepdim=True)) / xn
-    return loss, dx, dW
+    """oracle/chunked_fp32.py at this module's sizes (kept under its old name for the tests below)."""
+    from oracle.chunked_fp32 import chunked_reference
+    return chunked_reference(x, W, y, family=family, s=S, m=m, chunk=CHUNK)
 
 
 def test_bench_size_cosface_dc_layout_matches_fp32_torch():

@@ -64,3 +64,22 @@ def test_linearity_in_grad_scale():
     a = mo.loss_and_grads(cfg, mo.HeadState(), x, W, labels, grad_scale=1.0)
     b = mo.loss_and_grads(cfg, mo.HeadState(), x, W, labels, grad_scale=1024.0)
     assert rel(b["dx"], a["dx"] * 1024.0) < 1e-12 and rel(b["dW"], a["dW"] * 1024.0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["arcface", "cosface"])
+def test_chunked_reference_matches_golden(name):
+    """Pins the chunked fp32 checker to the reference: it must reproduce the committed golden (outputs of the
+    unmodified reference head + CrossEntropyLoss + autograd) at a small size, evaluated in 3 ragged chunks."""
+    from oracle.chunked_fp32 import chunked_reference, cosine
+    import os
+    from tests.helpers import GOLDEN_DIR, load_golden
+    g = load_golden(os.path.join(GOLDEN_DIR, name + ".npz"))
+    assert g["grad_scale"] == 1.0 and not g["cfg"].easy_margin
+    x, W, y = g["x"].float(), g["W"].float(), g["labels"]
+    Wc = W if name == "arcface" else W.t().contiguous()
+    loss, dx, dWc = chunked_reference(x, Wc, y, family=name, s=g["cfg"].s, m=g["cfg"].m, chunk=(Wc.shape[0] + 2) // 3)
+    dW = dWc if name == "arcface" else dWc.t()
+    assert abs(float(loss) - g["loss_id"]) <= 1e-5 * abs(g["loss_id"]), (float(loss), g["loss_id"])
+    assert cosine(dx.cpu(), g["dx"]) > 1 - 1e-9 and cosine(dW.cpu(), g["dW"]) > 1 - 1e-9
+    assert float((dx.cpu().double() - g["dx"].double()).norm() / g["dx"].double().norm()) < 1e-4
+    assert float((dW.cpu().double() - g["dW"].double()).norm() / g["dW"].double().norm()) < 1e-4

@@ -14,9 +14,10 @@ from .heads import (AdaFace, ArcFace, CosFace, CurricularFace, ElasticArcFace, E
 from .functional import HeadEngine, ShardInfo
 from .sharded import ShardedMarginHead, ShardComm, shard_range
 from . import _lib
+from ._lib import MarginHeadError
 from . import verification
 from .optim import HeadSGD
 
 __all__ = ["AdaFace", "ArcFace", "CosFace", "CurricularFace", "ElasticArcFace", "ElasticCosFace", "FusedOutput",
-           "HEAD_CLASSES", "MagFace", "MV_Softmax", "SphereFace", "VPLArcFace", "HeadEngine", "ShardInfo", "ShardedMarginHead", "ShardComm", "shard_range", "_lib", "verification",
+           "HEAD_CLASSES", "MagFace", "MarginHeadError", "MV_Softmax", "SphereFace", "VPLArcFace", "HeadEngine", "ShardInfo", "ShardedMarginHead", "ShardComm", "shard_range", "_lib", "verification",
            "HeadSGD"]

@@ -51,7 +51,7 @@ SIGNATURES = {
     "mh_device_check": [],
     "mh_prologue_w": [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp],
     "mh_sgd_step_w": [_vp, _i32, _i64, _i64, _vp, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _i64, _vp, _vp],
-    "mh_prologue_x": [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "mh_prologue_x": [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "mh_row_params": [_cfgp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
                                                          const float* __restrict__ inv_norm,
                                                          __nv_bfloat16* __restrict__ xhat, float* __restrict__ xhat32,
                                                          float* __restrict__ xnorm, float* __restrict__ t_raw,
-                                                         int32_t* __restrict__ label_local, int strict_labels) {
+                                                         int32_t* __restrict__ label_local, int64_t c_total) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B_pad) return;
@@ -583,9 +583,11 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
   dot = warp_sum(dot);
   if (lane == 0) {
     xnorm[row] = nrm;
-    // strict_labels (unsharded head): a label outside [0, C) poisons the row's target cosine, so the loss comes out NaN
-    // instead of silently dropping the target (the reference's one_hot.scatter_ raises a device assert there)
-    t_raw[row] = owned ? dot * inv_norm[y] : (strict_labels ? __int_as_float(0x7fc00000) : 0.f);
+    // a label outside [0, c_total) (the whole head, all shards) poisons the row's target cosine, so the loss comes out
+    // NaN instead of silently dropping the target (the reference's one_hot.scatter_ raises a device assert there);
+    // sharded: a valid label owned by another rank contributes 0 to the all-reduce(SUM) of t_raw, NaN survives it
+    const bool valid = labels[row] >= 0 && labels[row] < c_total;
+    t_raw[row] = owned ? dot * inv_norm[y] : (valid ? 0.f : __int_as_float(0x7fc00000));
     label_local[row] = owned ? (int32_t)y : -1;
   }
 }
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
 extern "C" int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pad, const int64_t* labels,
                              const float* W, int layout, int64_t C, int64_t ld, int64_t c_offset,
                              const float* inv_norm, void* x_hat_bf16, float* x_hat32, float* xnorm, float* t_raw,
-                             int32_t* label_local, int strict_labels, void* stream) {
+                             int32_t* label_local, int64_t c_total, void* stream) {
   MH_CHECK_ARG(x && labels && W && inv_norm && x_hat_bf16 && x_hat32 && xnorm && t_raw && label_local, "null pointer");
   MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % MH_TILE == 0, "B_pad must be a multiple of 128 and >= B");
   MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
@@ -603,13 +605,13 @@ extern "C" int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pa
   __nv_bfloat16* xh = (__nv_bfloat16*)x_hat_bf16;
   if (x_dtype == MH_F32)
     prologue_x_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
-                                                   inv_norm, xh, x_hat32, xnorm, t_raw, label_local, strict_labels);
+                                                   inv_norm, xh, x_hat32, xnorm, t_raw, label_local, c_total);
   else if (x_dtype == MH_BF16)
     prologue_x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, B_pad, labels, W, layout, C, ld,
-                                                           c_offset, inv_norm, xh, x_hat32, xnorm, t_raw, label_local, strict_labels);
+                                                           c_offset, inv_norm, xh, x_hat32, xnorm, t_raw, label_local, c_total);
   else if (x_dtype == MH_F16)
     prologue_x_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
-                                                    inv_norm, xh, x_hat32, xnorm, t_raw, label_local, strict_labels);
+                                                    inv_norm, xh, x_hat32, xnorm, t_raw, label_local, c_total);
   else
     MH_CHECK_ARG(false, "unknown x dtype");
   MH_LAUNCH_OK();

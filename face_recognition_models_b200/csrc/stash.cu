@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(256) stash_dx_combine_kernel(const float* __re
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B) return;
-  const float r = rho[row], g = gty[row];
-  const int32_t y = label_local[row];
+  // rho == NULL: plain sum of the split-K partials (recompute mode, before the cross-rank reduce-scatter)
+  const float r = rho ? rho[row] : 1.f, g = rho ? gty[row] : 0.f;
+  const int32_t y = rho ? label_local[row] : -1;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(256) stash_dx_combine_kernel(const float* __re
 extern "C" int mh_stash_dx_combine(const float* dxhat_part, int n_split, int64_t split_stride, const float* rho,
                                    const float* gty, const int32_t* label_local, const void* w_hat_bf16, int64_t B,
                                    float* dxhat, void* stream) {
-  MH_CHECK_ARG(dxhat_part && rho && gty && label_local && w_hat_bf16 && dxhat, "null pointer");
+  MH_CHECK_ARG(dxhat_part && dxhat, "null pointer");
+  MH_CHECK_ARG(!rho || (gty && label_local && w_hat_bf16), "the stash terms need rho, gty, label_local and w_hat together");
   MH_CHECK_ARG(n_split >= 1 && B > 0, "bad shape");
   stash_dx_combine_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       dxhat_part, n_split, split_stride, rho, gty, label_local, (const __nv_bfloat16*)w_hat_bf16, B, dxhat);

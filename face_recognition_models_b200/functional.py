@@ -82,6 +82,7 @@ class ShardInfo:
     rank: int = 0
     world: int = 1
     c_offset: int = 0
+    c_total: int = 0              # class count of the whole head (0: unsharded, = the engine's C)
 
 
 class HeadEngine:
@@ -236,7 +237,7 @@ class HeadEngine:
         label_local = self._buf("label_local", (B_pad,), torch.int32, dev)
         L.call("mh_prologue_x", _ptr(x), _DT[x.dtype], B, B_pad, _ptr(labels), _ptr(W), self.layout, Cn, ld,
                self.shard.c_offset, _ptr(inv_norm), _ptr(x_hat), _ptr(x_hat32), _ptr(xnorm), _ptr(t_raw),
-               _ptr(label_local), 1 if self.shard.world == 1 else 0, st)
+               _ptr(label_local), self.shard.c_total or Cn, st)
         if self.shard.world > 1:
             # every rank needs every row's target cosine (thresholds, EMA); only the owner computed it
             self.shard.comm.allreduce_sum_(t_raw)
@@ -429,8 +430,12 @@ class HeadEngine:
             R = self.shard.world
             assert B % R == 0
             Bl = B // R
-            full = part[:, :B].sum(dim=0) if n_split > 1 else part[0, :B]
-            mine = self.shard.comm.reduce_scatter_rows(full.contiguous())
+            if n_split > 1:               # recompute mode: sum the split-K partials with the combine kernel (rho = NULL)
+                full = self._buf("dxhat_full", (1, ctx["B_pad"], L.D), torch.float32, dev)
+                L.call("mh_stash_dx_combine", _ptr(part), n_split, split_stride, _ptr(None), _ptr(None), _ptr(None),
+                       _ptr(None), B, _ptr(full), st)
+                part = full
+            mine = self.shard.comm.reduce_scatter_rows(part[0, :B])    # a contiguous view: no copy
             r0 = self.shard.rank * Bl
             dx = torch.empty((Bl, L.D), dtype=ctx["x_dtype"], device=dev)
             rowp_off = ctx["rowp"][:, r0:]

@@ -130,13 +130,18 @@ class ShardedMarginHead(nn.Module):
         self.comm = ShardComm(group)
         self.dx_scale = float(dx_scale)
         b, e = shard_range(num_classes, self.comm.world, self.comm.rank)
+        smallest = min(e_ - b_ for b_, e_ in (shard_range(num_classes, self.comm.world, r) for r in range(self.comm.world)))
+        if smallest < 2:            # the same verdict on every rank (a rank raising alone would hang the others)
+            raise ValueError(f"ShardedMarginHead: {num_classes} classes in chunks of ceil(C/R) over {self.comm.world} ranks "
+                             f"leave a rank with {smallest} classes; every rank needs at least 2 - use fewer ranks")
         self.c_begin, self.c_end = b, e
         cls = HEAD_CLASSES[family]
         if family in ("mv_am", "mv_arc"):
             ctor_kwargs = dict(ctor_kwargs, margin_type="am" if family == "mv_am" else "arc")
         # build the local shard with the reference initialisation, then rebind its engine to the shard
         self.local = cls(512, e - b, **ctor_kwargs)
-        self.local._engine.shard = ShardInfo(comm=self.comm, rank=self.comm.rank, world=self.comm.world, c_offset=b)
+        self.local._engine.shard = ShardInfo(comm=self.comm, rank=self.comm.rank, world=self.comm.world, c_offset=b,
+                                             c_total=num_classes)
         self.local._engine.mode = mode
         self.engine: HeadEngine = self.local._engine
 

@@ -140,12 +140,13 @@ int mh_sgd_step_w(float* W, int layout, int64_t C, int64_t ld, const float* grad
  * cosine gather (criterion.py:417,552).  labels are GLOBAL class ids (int64); this shard owns
  * [c_offset, c_offset + C).  Outputs: x_hat bf16 [B_pad,512] (rows >= B zeroed), x_hat32 fp32
  * [B,512], xnorm[B], t_raw[B] = <x_hat_i, w_hat_{y_i}> in fp32 (0 when the label is not owned),
- * label_local[B_pad] (int32; -1 when not owned or row >= B).  strict_labels != 0 (unsharded head): a label outside
- * [0, C) sets t_raw to NaN so that the loss is NaN (the reference's one_hot.scatter_ fails on such a label). */
+ * label_local[B_pad] (int32; -1 when not owned or row >= B).  c_total = class count of the WHOLE head (= C when
+ * unsharded): a label outside [0, c_total) sets t_raw to NaN so that the loss is NaN on every rank (NaN survives the
+ * all-reduce of t_raw; the reference's one_hot.scatter_ fails on such a label, criterion.py:290-291). */
 int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pad, const int64_t* labels,
                   const float* W, int layout, int64_t C, int64_t ld, int64_t c_offset,
                   const float* inv_norm, void* x_hat_bf16, float* x_hat32, float* xnorm, float* t_raw,
-                  int32_t* label_local, int strict_labels, void* stream);
+                  int32_t* label_local, int64_t c_total, void* stream);
 
 /* Per-row margin terms + batch-global state updates (CurricularFace EMA criterion.py:570-573,
  * AdaFace batch statistics criterion.py:876-885, MagFace loss_g criterion.py:1248).  margins may be
@@ -235,7 +236,8 @@ int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_
 int mh_stash_prep(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
                   const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty, void* stream);
 
-/* dxhat [B, 512] = rho_i * sum_splits dxhat_part + gty_i * w^_{y_i} (target term only where label_local >= 0). */
+/* dxhat [B, 512] = rho_i * sum_splits dxhat_part + gty_i * w^_{y_i} (target term only where label_local >= 0).
+ * rho == NULL: the plain sum of the split-K partials (gty / label_local / w_hat ignored; recompute mode, sharded). */
 int mh_stash_dx_combine(const float* dxhat_part, int n_split, int64_t split_stride, const float* rho, const float* gty,
                         const int32_t* label_local, const void* w_hat_bf16, int64_t B, float* dxhat, void* stream);
 

@@ -1,5 +1,6 @@
-"""GPU, 2 ranks, NCCL: the class-sharded head equals the single-GPU head on the concatenated batch.
-Run on a multi-GPU box: pytest -m gpu tests/test_gpu_sharded.py (skipped when fewer than 2 GPUs)."""
+"""GPU, 2 and 8 ranks, NCCL: the class-sharded head equals the oracle on the concatenated batch (loss, accuracy, dx after
+the reduce-scatter, the shard's dW), in both backward modes; HeadSGD on the shards; bad labels; the device guard.
+Run on a multi-GPU box: pytest -m gpu tests/test_gpu_sharded.py (a case is skipped when the box has fewer GPUs)."""
 import os
 import socket
 
@@ -19,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, fam, q):
+def _worker(rank, world, port, fam, bmode, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -28,13 +29,14 @@ def _worker(rank, world, port, fam, q):
         import face_recognition_models_b200 as pkg
         from oracle import margin_oracle as mo
         from tests.helpers import build_head, cosim, prime_head, rel
-        Bl, Cn = 96, 5000
+        Bl, Cn = 96, 5003                       # ragged last shard at 2 and at 8 ranks (2502/2501, 7 x 626 + 621)
         cfg = mo.HeadConfig.default(fam)
         x, W, labels = mo.make_inputs(fam, Bl * world, Cn, 512, seed=77)
         ref = mo.loss_and_grads(cfg, mo.HeadState(), x, W, labels)
         kw = dict(arcface=dict(s=cfg.s, m=cfg.m, easy_margin=False), curricularface=dict(m=cfg.m, s=cfg.s, momentum=cfg.momentum),
-                  cosface=dict(s=cfg.s, m=cfg.m))[fam]
+                  cosface=dict(s=cfg.s, m=cfg.m), mv_am=dict(margin=cfg.m, mv_weight=cfg.mv_weight, s=cfg.s))[fam]
         head = pkg.ShardedMarginHead(fam, Cn, **kw).cuda()
+        head.engine.backward_mode = bmode
         b, e = head.c_begin, head.c_end
         Wc = W if mo.LAYOUT[fam] == "CD" else W.t()
         shard = Wc[b:e] if mo.LAYOUT[fam] == "CD" else Wc[b:e].t()
@@ -59,15 +61,83 @@ def _worker(rank, world, port, fam, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fam", ["arcface", "curricularface", "cosface"])
-def test_two_gpu_sharded_matches_oracle(fam):
+def _bad_label_worker(rank, world, port, q):
+    """A label outside [0, C) must poison the loss on EVERY rank (no silent drop of the target, no hang)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import face_recognition_models_b200 as pkg
+        head = pkg.ShardedMarginHead("arcface", 1000, s=64.0, m=0.5, easy_margin=False).cuda()
+        g = torch.Generator(device="cuda").manual_seed(5 + rank)
+        x = torch.randn(8, 512, device="cuda", generator=g)
+        y = torch.randint(0, 1000, (8,), device="cuda", generator=g)
+        ok = head.fused_loss(x, y)
+        assert bool(torch.isfinite(ok.loss))
+        if rank == world - 1:
+            y[3] = 1000                          # one bad label on one rank
+        bad = head.fused_loss(x, y)
+        assert bool(torch.isnan(bad.loss)), float(bad.loss)
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_bad_label_poisons_every_rank():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, fam, q)) for r in range(world)]
+    procs = [ctx.Process(target=_bad_label_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_head_on_non_current_device():
+    """a head on cuda:1 must work while cuda:0 is the current device (streams, workspaces and launches follow
+    the data), like the reference's modules."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import face_recognition_models_b200 as pkg
+    from oracle import margin_oracle as mo
+    from tests.helpers import cosim
+    torch.cuda.set_device(0)
+    x, W, labels = mo.make_inputs("cosface", 64, 1000, 512, seed=3)
+    ref = mo.loss_and_grads(mo.HeadConfig.default("cosface"), mo.HeadState(), x, W, labels)
+    head = pkg.CosFace(512, 1000, s=64.0, m=0.35).to("cuda:1")       # DC layout: > 48 KB dynamic smem prologue on device 1
+    with torch.no_grad():
+        head.kernel.copy_(W.to("cuda:1"))
+    xg = x.to("cuda:1").requires_grad_(True)
+    out = head.fused_loss(xg, labels.to("cuda:1"))
+    out.loss.backward()
+    torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
+    assert abs(float(out.loss) - float(ref["loss"])) < 2e-3 * abs(float(ref["loss"]))
+    assert cosim(xg.grad, ref["dx"]) > 0.9995 and cosim(head.kernel.grad, ref["dW"]) > 0.9995
+    with pytest.raises(pkg.MarginHeadError, match="share one device"):
+        head.fused_loss(xg, labels.to("cuda:0"))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("fam,bmode", [("arcface", "auto"), ("arcface", "recompute"), ("curricularface", "auto"),
+                                       ("cosface", "auto"), ("mv_am", "auto")])
+def test_sharded_matches_oracle(fam, bmode, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fam, bmode, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]

@@ -115,3 +115,35 @@ def test_head_sgd_host_side():
     eng._shadow = (1, 2, 3)
     eng.invalidate_shadow()
     assert eng._shadow is None
+
+
+def test_sharded_head_rejects_shards_that_are_too_small():
+    """chunks of ceil(C/R) can leave trailing ranks with no classes; every rank must refuse, not one."""
+    from face_recognition_models_b200.sharded import shard_range
+    # world 8, C = 9: chunks of 2 -> ranks 5..7 own 1, 0, 0 classes
+    sizes = [e - b for b, e in (shard_range(9, 8, r) for r in range(8))]
+    assert min(sizes) == 0 and sum(sizes) == 9
+    import face_recognition_models_b200.sharded as sh
+
+    class _Comm:                     # a ShardComm stand-in for rank 0 of 8 (no process group needed)
+        group, world, rank, _backend = None, 8, 0, "none"
+    real = sh.ShardComm
+    sh.ShardComm = lambda group=None: _Comm()
+    try:
+        with pytest.raises(ValueError, match="at least 2"):
+            pkg.ShardedMarginHead("arcface", 9, s=64.0, m=0.5, easy_margin=False)
+        head = pkg.ShardedMarginHead("arcface", 64, s=64.0, m=0.5, easy_margin=False)       # 8 classes per rank: fine
+        assert head.engine.shard.c_total == 64 and head.engine.shard.c_offset == 0
+    finally:
+        sh.ShardComm = real
+
+
+def test_mh_lib_env_selects_the_library(tmp_path, monkeypatch):
+    """MH_LIB must be honoured by _lib.load() (variant builds for A/B runs), and a bad path must fail loudly."""
+    from face_recognition_models_b200 import _lib as L
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setenv("MH_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(L.MarginHeadError, match="nope.so"):
+        L.load()
+    monkeypatch.setenv("MH_LIB", L.LIB_PATH)
+    assert L.load() is not None

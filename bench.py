@@ -660,6 +660,7 @@ def run_b200(args):
         "mh_tc_forward": ("tensor", gemm_flops), "mh_tc_backward_g": ("tensor", gemm_flops),
         "mh_tc_backward_dx": ("tensor", gemm_flops), "mh_tc_backward_dw": ("tensor", gemm_flops),
         "mh_tc_backward_dw_fused": ("tensor", gemm_flops), "mh_tc_backward_dx_stash": ("tensor", gemm_flops),
+        "mh_tc_backward_dw_proj": ("tensor", gemm_flops),
         "mh_prologue_w": ("hbm", 6.0 * C_loc * D + 4.0 * C_loc),
         "mh_norm_backward_w": ("hbm", (4.0 + 2.0 + 4.0) * C_loc * D),
     }

@@ -27,6 +27,20 @@ class MhConfig(C.Structure):
     ]
 
 
+class MhStepWs(C.Structure):
+    """Mirror of ``mh_step_ws`` in include/margin_head.h (workspace descriptor of mh_step_forward / mh_step_backward)."""
+    _fields_ = [
+        ("B", C.c_int64), ("B_pad", C.c_int64), ("C", C.c_int64), ("C_pad", C.c_int64), ("ld", C.c_int64),
+        ("layout", C.c_int32), ("x_dtype", C.c_int32),
+        ("w_hat", C.c_void_p), ("inv_norm", C.c_void_p), ("x_hat", C.c_void_p), ("x_hat32", C.c_void_p),
+        ("xnorm", C.c_void_p), ("t_raw", C.c_void_p), ("label_local", C.c_void_p), ("rowp", C.c_void_p),
+        ("stats_tiles", C.c_void_p), ("n_tiles", C.c_int64), ("merge_scratch", C.c_void_p), ("stats", C.c_void_p),
+        ("rowout", C.c_void_p), ("bc", C.c_void_p), ("xs", C.c_void_p), ("rho", C.c_void_p), ("gty", C.c_void_p),
+        ("dxhat_part", C.c_void_p), ("part_splits", C.c_int64), ("dxhat_full", C.c_void_p), ("gscal", C.c_void_p),
+        ("r_colsum", C.c_void_p), ("rpart", C.c_void_p), ("rflag", C.c_void_p), ("dx_sync", C.c_void_p),
+    ]
+
+
 # enums of include/margin_head.h
 FAMILY = dict(arcface=0, cosface=1, sphereface=2, mv_am=3, mv_arc=4, curricularface=5, adaface=6,
               elastic_cos=7, elastic_arc=8, magface=9, vpl_arcface=10)
@@ -39,6 +53,7 @@ RO = dict(LSE2=0, LOSS=1, CNT=2, AUX0=3, AUX1=4)
 RO_PLANES = 5
 STATE_FLOATS = 8
 MERGE_BLOCKS = 64
+DX_SYNC_INTS = 64
 TILE = 128
 NTILE = 256
 D = 512
@@ -56,15 +71,18 @@ SIGNATURES = {
     "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i64, _vp],
-    "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mh_tc_backward_dw_proj": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp],
+    "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, C.POINTER(C.c_int), _vp, _vp],
     "mh_vpl_mix": [_vp, _vp, _vp, C.c_float, _i64, _i64, _vp, _vp, _vp],
     "mh_pair_cosine": [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp],
+    "mh_step_forward": [_cfgp, C.POINTER(MhStepWs), _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
+    "mh_step_backward": [_cfgp, C.POINTER(MhStepWs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_fixref_ok": [_cfgp, _i64],
     "mh_tc_stash_ok": [_cfgp, _i64],
     "mh_stash_prep": [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "mh_stash_dx_combine": [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "mh_stash_dw_target": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
-    "mh_tc_backward_dx": [_vp, _i64, _i64, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mh_tc_backward_dx": [_vp, _i64, _i64, _vp, _vp, C.POINTER(C.c_int), _vp, _vp],
     "mh_tc_backward_dw": [_vp, _i64, _i64, _vp, _vp, _vp],
     "mh_sgemm_strided": [_i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp],
     "mh_dense_forward": [_cfgp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -130,6 +148,11 @@ def _launches(name: str, args) -> int:
         return 0 if not getattr(args[4], "value", None) else 1
     if name == "mh_tc_backward_dx_stash":
         return 0 if not getattr(args[9], "value", None) else 1
+    if name == "mh_step_forward":
+        return 6 + (1 if int(args[8]) else 0)              # x prologue, row terms, identity fill, forward, merge, finalize (+ W prologue)
+    if name == "mh_step_backward":
+        stash, dx, dw = int(args[2]), bool(getattr(args[6], "value", None)), bool(getattr(args[7], "value", None))
+        return 1 + (1 if stash else 1) + ((3 if stash else 2) if dx else 0) + ((3 if stash else 2) if dw else 0)
     return 1
 
 

@@ -1,0 +1,103 @@
+// One C call per phase of a training step (single GPU, tensor-core path): mh_step_forward / mh_step_backward enqueue the
+// whole kernel sequence that face_recognition_models_b200/functional.py otherwise drives entry point by entry point
+// (~20 FFI calls per step).  BASELINE configs 2 and 3 (B=512, C=10,575 / B=1024, C=85,742) are launch-bound: their
+// kernels sum to 0.1-0.4 ms while the per-call host overhead of the Python driver was 0.4-0.6 ms.  Nothing new runs on the
+// device here: these are the same entry points of include/margin_head.h in the same order, sharing one workspace
+// descriptor (mh_step_ws, all caller-owned device pointers).
+#include "common.cuh"
+
+#define STEP_TRY(call)                 \
+  do {                                 \
+    if (int _e = (call)) return _e;    \
+  } while (0)
+
+static int check_ws(const mh_step_ws* ws) {
+  MH_CHECK_ARG(ws, "null workspace descriptor");
+  MH_CHECK_ARG(ws->B > 0 && ws->B_pad >= ws->B && ws->B_pad % 256 == 0, "B_pad must be a multiple of 256 and >= B");
+  MH_CHECK_ARG(ws->C > 0 && ws->C_pad >= ws->C && ws->C_pad % 256 == 0, "C_pad must be a multiple of 256 and >= C");
+  MH_CHECK_ARG(ws->w_hat && ws->inv_norm && ws->x_hat && ws->x_hat32 && ws->xnorm && ws->t_raw && ws->label_local &&
+                   ws->rowp && ws->stats_tiles && ws->merge_scratch && ws->stats && ws->rowout,
+               "null forward workspace pointer");
+  return MH_OK;
+}
+
+extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const void* x, const int64_t* labels,
+                               const float* W, const float* margins, float* state, int update_state, int run_prologue_w,
+                               int stash, float* scalars, void* stream) {
+  MH_CHECK_ARG(cfg && x && labels && W && state && scalars, "null pointer");
+  STEP_TRY(check_ws(ws));
+  MH_CHECK_ARG(!stash || ws->bc, "stash requested without a B x C buffer");
+  MH_CHECK_ARG(ws->n_tiles == mh_fwd_num_tiles(ws->C_pad), "stats_tiles must hold mh_fwd_num_tiles records");
+  if (run_prologue_w)
+    STEP_TRY(mh_prologue_w(W, ws->layout, ws->C, ws->ld, ws->w_hat, ws->C_pad, nullptr, ws->inv_norm, stream));
+  STEP_TRY(mh_prologue_x(x, ws->x_dtype, ws->B, ws->B_pad, labels, W, ws->layout, ws->C, ws->ld, /*c_offset=*/0,
+                         ws->inv_norm, ws->x_hat, ws->x_hat32, ws->xnorm, ws->t_raw, ws->label_local, /*c_total=*/ws->C,
+                         stream));
+  STEP_TRY(mh_row_params(cfg, ws->B, ws->xnorm, ws->t_raw, margins, state, update_state, ws->rowp, ws->B_pad, stream));
+  STEP_TRY(mh_tc_forward(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                         ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr, stream));
+  STEP_TRY(mh_merge_stats(ws->stats_tiles, ws->n_tiles, ws->B, ws->B_pad, ws->merge_scratch, ws->stats, stream));
+  STEP_TRY(mh_finalize_rows(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, cfg->family == MH_SPHEREFACE ? 1 : 0,
+                            ws->rowout, ws->B_pad, scalars, state, stream));
+  return MH_OK;
+}
+
+extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int stash, const float* state,
+                                const float* g_loss, const float* g_lossg, void* dx, float* dW, void* stream) {
+  MH_CHECK_ARG(cfg && state, "null pointer");
+  STEP_TRY(check_ws(ws));
+  MH_CHECK_ARG(ws->bc && ws->gscal && ws->dxhat_part, "null backward workspace pointer");
+  MH_CHECK_ARG(ws->r_colsum || (ws->rpart && ws->rflag), "need r_colsum (side-pass projection) or rpart + rflag (self-projection)");
+  MH_CHECK_ARG(!stash || (ws->xs && ws->rho && ws->gty && ws->dxhat_full), "null stash workspace pointer");
+  const float* rowout = ws->rowout;
+  const float* aux0 = rowout + (int64_t)MH_RO_AUX0 * ws->B_pad;
+  const float* aux1 = rowout + (int64_t)MH_RO_AUX1 * ws->B_pad;
+  const float* lse2 = rowout + (int64_t)MH_RO_LSE2 * ws->B_pad;
+  // projection term r_j = w^_j . dw^_j of the dW epilogue: either produced beforehand (stash: the dx kernel's side pass,
+  // one partial per 128-row block; recompute: the backward-G column sums) or taken from the dW accumulators themselves
+  const bool selfp = ws->r_colsum == nullptr;
+  const int r_parts = stash ? (int)(ws->B_pad / MH_TILE) : 1;
+  STEP_TRY(mh_make_gscal(g_loss, g_lossg, ws->B, ws->gscal, stream));
+  int n_split = 0;
+  STEP_TRY(mh_tc_backward_dx(nullptr, ws->B_pad, ws->C_pad, nullptr, nullptr, &n_split, nullptr, stream));
+  MH_CHECK_ARG(n_split <= ws->part_splits, "dxhat_part holds fewer splits than mh_tc_backward_dx needs");
+  const int64_t split_stride = ws->B_pad * MH_D;
+  const void* xs = ws->x_hat;
+  if (stash) {
+    STEP_TRY(mh_stash_prep(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
+                           ws->gty, stream));
+    xs = ws->xs;
+    if (selfp) {
+      if (dx) STEP_TRY(mh_tc_backward_dx(ws->bc, ws->B_pad, ws->C_pad, ws->w_hat, ws->dxhat_part, &n_split, ws->dx_sync, stream));
+    } else if (dx || dW) {          // the side pass of this GEMM feeds dW's projection: it runs even when only dW is wanted
+      STEP_TRY(mh_tc_backward_dx_stash(cfg, ws->bc, ws->B_pad, ws->C, ws->C_pad, ws->w_hat, ws->rho, ws->rowp, ws->B_pad,
+                                       ws->dxhat_part, ws->r_colsum, &n_split, ws->dx_sync, stream));
+    }
+    if (dx) {
+      STEP_TRY(mh_stash_dx_combine(ws->dxhat_part, n_split, split_stride, ws->rho, ws->gty, ws->label_local, ws->w_hat,
+                                   ws->B, ws->dxhat_full, stream));
+      STEP_TRY(mh_norm_backward_x(ws->dxhat_full, 1, split_stride, ws->x_hat32, ws->xnorm, ws->rowp, ws->B_pad, aux0, aux1,
+                                  ws->gscal, ws->B, dx, ws->x_dtype, stream));
+    }
+  } else {
+    STEP_TRY(mh_tc_backward_g(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                              ws->label_local, state, lse2, ws->bc, (dW && !selfp) ? ws->r_colsum : nullptr, stream));
+    if (dx) {
+      STEP_TRY(mh_tc_backward_dx(ws->bc, ws->B_pad, ws->C_pad, ws->w_hat, ws->dxhat_part, &n_split, ws->dx_sync, stream));
+      STEP_TRY(mh_norm_backward_x(ws->dxhat_part, n_split, split_stride, ws->x_hat32, ws->xnorm, ws->rowp, ws->B_pad, aux0,
+                                  aux1, ws->gscal, ws->B, dx, ws->x_dtype, stream));
+    }
+  }
+  if (dW) {
+    if (selfp)
+      STEP_TRY(mh_tc_backward_dw_proj(ws->bc, ws->B_pad, ws->C, ws->C_pad, xs, ws->w_hat, ws->inv_norm, ws->gscal,
+                                      ws->layout, dW, ws->ld, ws->rpart, ws->rflag, stream));
+    else
+      STEP_TRY(mh_tc_backward_dw_fused(ws->bc, ws->B_pad, ws->C, ws->C_pad, xs, ws->w_hat, ws->inv_norm, ws->r_colsum,
+                                       r_parts, ws->gscal, ws->layout, dW, ws->ld, stream));
+    if (stash)
+      STEP_TRY(mh_stash_dw_target(ws->gty, ws->label_local, ws->x_hat32, ws->w_hat, ws->inv_norm, ws->gscal, ws->B,
+                                  ws->layout, dW, ws->ld, stream));
+  }
+  return MH_OK;
+}

@@ -34,6 +34,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int DX_SYNC_KB = 16;                    // DX lockstep: k-blocks between two rendezvous of a split's CTAs
 constexpr int STG_WARP_BYTES = 32 * 128;          // output staging per epilogue warp: 32 rows x 128 B, XOR-swizzled
 
 enum { MODE_FWD = 0, MODE_FWDS = 1, MODE_BWD_G = 2, MODE_DX = 3, MODE_DW = 4 };
@@ -79,6 +80,9 @@ struct TcArgs {
   float* rsum;                 // r_j: BWD_G accumulates [C_pad] (atomics); DX (stash) stores one partial per 128-row block
                                // ([B_pad/128][C_pad], plain stores: reproducible); DW fused sums rsum_parts partials
   int rsum_parts;              // DW fused: number of partial planes of rsum (1 for the BWD_G sums)
+  float* rpart;                // DW self-projection: [4][C_pad] partial dots w^_j . dw^_j (d half x epilogue column half)
+  int* rflag;                  // DW self-projection: [C_pad/128] arrival counters, zeroed before the launch
+  int* dx_sync;                // DX lockstep: [n_split] arrival counters (NULL: off), zeroed before the launch
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
   int side_mv;                 // DX side pass, MV-Softmax: invert the hard-negative re-weighting u = a*c + b as well
@@ -157,6 +161,17 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// named barrier among the epilogue warps only (barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---- cta_group::2 (SM pair) variants -----------------------------------------------------------------
@@ -658,6 +673,21 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         ++tile_j;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          if (MODE == MODE_DX && a.dx_sync && ((kb - w.kb0) & (DX_SYNC_KB - 1)) == 0) {
+            // lockstep among the 2 * m_tiles CTAs that stream the same w^ k-blocks (one split, all row tiles): nobody
+            // starts k-block group g before everybody has issued group g-1, so a w^ tile fetched from HBM for one row
+            // tile is still in L2 for the others (ncu: 7.6 GB read for 6.15 GB algorithmic without it).  Single wave only
+            // (host-checked: every tile is resident), bounded spin.
+            int* ctr = a.dx_sync + w.split;
+            const int target = ((kb - w.kb0) / DX_SYNC_KB) * 2 * a.m_tiles;
+            red_release_gpu_add(ctr, 1);
+            if (ld_acquire_gpu(ctr) < target) {
+              const long long t0 = clock64();
+              while (ld_acquire_gpu(ctr) < target) {
+                if (clock64() - t0 > 4000000000LL) __trap();
+              }
+            }
+          }
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (MODE == MODE_DX && a.rho) mbar_wait(bar_rdone + 8 * stage, phase ^ 1);   // side pass has read the A tile
           const uint32_t sa = tiles_base + stage * STAGE_BYTES;
@@ -922,9 +952,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // ---- DW: this thread owns class `row` and 128 of the tile's 256 d columns ----
         const bool raw = a.raw_dw != 0;
         const bool ok = raw || row < a.C;
+        const bool selfp = !raw && a.rpart != nullptr;
         float rj = 0.f, coef = 1.f;
         if (!raw && row < a.C) {
-          for (int pp = 0; pp < a.rsum_parts; ++pp) rj += a.rsum[(int64_t)pp * a.C_pad + row];   // fixed order
+          if (!selfp)
+            for (int pp = 0; pp < a.rsum_parts; ++pp) rj += a.rsum[(int64_t)pp * a.C_pad + row];   // fixed order
           coef = a.gscal[0] * a.inv_norm[row];
         }
         if (!raw && row >= a.C) coef = 0.f;
@@ -933,6 +965,52 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(bar_tfull + 8 * buf, bphase);
         tc_fence_after();
         if (!raw) mbar_wait(bar_wfull, it & 1);            // this tile's w^ [128 classes][256 d] is in shared memory
+        if (selfp) {
+          // ---- self-projection: r_j = w^_j . dw^_j taken from the accumulators themselves.  This thread owns class `row`
+          // and 128 of the 512 d columns (d half of the tile x column half of the warp); the four partial dots of a class
+          // live in two CTA pairs (the tiles 2k / 2k+1 = the two d halves of one class tile run on neighbouring pairs at
+          // the same time).  Every partial is posted to global memory BEFORE anything waits, the wait is bounded, and
+          // the four partials are summed in a fixed order: no atomics on data, bit-reproducible, no deadlock by
+          // construction (a tile's post depends only on its own pair reaching it).
+          float p = 0.f;
+          chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
+            const int dcol = cbase + c * 32;
+            const uint32_t wrow_s = wtile_base + (dcol >> 6) * (BM * 128) + r * 128;
+            const int ci0 = (dcol & 63) >> 3;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              uint4 wq;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w)
+                           : "r"(wrow_s + (((ci0 + k4) ^ (r & 7)) << 4)));
+              const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+                const int k = k4 * 8 + e * 2;
+                p = fmaf(__uint_as_float(cur[k]), wf.x, p);
+                p = fmaf(__uint_as_float(cur[k + 1]), wf.y, p);
+              }
+            }
+          }, no_op);
+          const int plane = (w.n0 / BN) * 2 + half;
+          __stcg(a.rpart + (int64_t)plane * a.C_pad + row, p);
+          __threadfence();
+          epi_bar_sync();                                       // all 256 partials of this CTA are posted and fenced
+          int* flag = a.rflag + (w.m0 / BM);
+          if (warp == EPI_WARP0 && lane == 0) {
+            red_release_gpu_add(flag, 1);
+            if (ld_acquire_gpu(flag) < 2) {                     // the CTA holding the other d half of these 128 classes
+              const long long t0 = clock64();
+              while (ld_acquire_gpu(flag) < 2) {
+                if (clock64() - t0 > 4000000000LL) __trap();
+              }
+            }
+          }
+          epi_bar_sync();
+          rj = __ldcg(a.rpart + row) + __ldcg(a.rpart + a.C_pad + row) + __ldcg(a.rpart + 2 * a.C_pad + row) +
+               __ldcg(a.rpart + 3 * a.C_pad + row);
+        }
         chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
           float o[32];
           if (raw) {
@@ -1036,7 +1114,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cud
   }));
   const int units = num_sms() / 2;
   // A-stationary kernels use a static schedule over exactly `units` pairs (pairs without work exit at once)
-  const int n = mode_astat(MODE) ? units : (int)std::min<int64_t>(args.total_tiles, units);
+  int n = mode_astat(MODE) ? units : (int)std::min<int64_t>(args.total_tiles, units);
+  // DW: the two d halves of a class tile (tiles 2k, 2k+1) run on neighbouring pairs in the same sweep
+  if (MODE == MODE_DW && n > 1) n &= ~1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * n);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -1222,6 +1302,7 @@ struct DxSide {
   const float* rowp = nullptr;
   int64_t ldp = 0;
   float* rsum = nullptr;
+  int* sync_ws = nullptr;      // >= MH_DX_SYNC_INTS ints of scratch (NULL: no lockstep)
 };
 
 static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
@@ -1263,23 +1344,33 @@ static int tc_backward_dx_impl(const void* G_bf16, int64_t B_pad, int64_t C_pad,
   a.out = out; a.out_split_stride = B_pad * MH_D;
   a.rho = side.rho; a.side_kappa = side.kappa; a.side_inv_s2 = side.inv_s2; a.rsum = side.rsum;
   a.side_mv = side.mv; a.side_ha = side.ha; a.side_hb = side.hb; a.rowp = side.rowp; a.ldp = side.ldp;
+  // lockstep only when every tile is resident at once (one wave) and several row tiles share a split
+  static const int env_lock = [] { const char* e = getenv("MH_DX_LOCKSTEP"); return e ? atoi(e) : 0; }();
+  if (side.sync_ws && env_lock && m_tiles > 1 && a.total_tiles <= pairs && n_split <= MH_DX_SYNC_INTS) {
+    MH_CUDA_OK(cudaMemsetAsync(side.sync_ws, 0, sizeof(int) * n_split, (cudaStream_t)stream));
+    a.dx_sync = side.sync_ws;
+  }
   return launch<MODE_DX, V_NONE>(ta, tb, a, (cudaStream_t)stream);
 }
 
 extern "C" int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16, float* out,
-                                 int* n_split_host, void* stream) {
-  return tc_backward_dx_impl(G_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, DxSide{}, stream);
+                                 int* n_split_host, int* sync_ws, void* stream) {
+  DxSide side;
+  side.sync_ws = sync_ws;
+  return tc_backward_dx_impl(G_bf16, B_pad, C_pad, w_hat_bf16, out, n_split_host, side, stream);
 }
 
 extern "C" int mh_tc_backward_dx_stash(const mh_config* cfg_host, const void* stash_bf16, int64_t B_pad, int64_t C,
                                        int64_t C_pad, const void* w_hat_bf16, const float* rho, const float* rowp,
-                                       int64_t ldp, float* out, float* r_colsum, int* n_split_host, void* stream) {
+                                       int64_t ldp, float* out, float* r_colsum, int* n_split_host, int* sync_ws,
+                                       void* stream) {
   MH_CHECK_ARG(cfg_host, "null pointer");
   MH_CHECK_ARG(!out || (rho && r_colsum && rowp && ldp >= B_pad), "null pointer");
   MH_CHECK_ARG(mh_tc_stash_ok(cfg_host, C), "head not eligible for the stash backward (see mh_tc_stash_ok)");
   const MhParams p = mh_make_params(cfg_host);
   const float s2 = p.s * MH_LOG2E;
   DxSide side;
+  side.sync_ws = sync_ws;
   if (out) {
     side.rho = rho; side.kappa = (s2 * family_umax(p) - 102.f) / s2; side.inv_s2 = 1.f / s2; side.rsum = r_colsum;
     side.mv = (p.hard_kind == 1); side.ha = p.hard_a; side.hb = p.hard_b; side.rowp = rowp; side.ldp = ldp;
@@ -1324,5 +1415,23 @@ extern "C" int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_
   a.rsum = const_cast<float*>(r_colsum); a.rsum_parts = r_parts;
   MH_CHECK_ARG(r_parts >= 1, "r_parts must be >= 1");
   if (int e = make_tmap(&a.tmW, w_hat_bf16, C_pad, MH_D, BM)) return e;       // epilogue operand: boxes [64 d][128 classes]
+  return launch_dw(G_bf16, B_pad, C, C_pad, x_hat_bf16, a, (cudaStream_t)stream);
+}
+
+// dW with the projection taken from the accumulators (no r_colsum input): rpart_ws [4 * C_pad] floats, flag_ws
+// [C_pad / 128] ints, both scratch owned by the caller; flag_ws is zeroed here (stream-ordered).
+extern "C" int mh_tc_backward_dw_proj(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
+                                      const void* w_hat_bf16, const float* inv_norm, const float* gscal, int layout,
+                                      float* dW, int64_t ld, float* rpart_ws, int* flag_ws, void* stream) {
+  MH_CHECK_ARG(G_bf16 && x_hat_bf16 && w_hat_bf16 && inv_norm && gscal && dW && rpart_ws && flag_ws, "null pointer");
+  MH_CHECK_ARG(B_pad > 0 && B_pad % BM == 0 && C_pad > 0 && C_pad % BN == 0 && C > 0 && C <= C_pad, "bad padded shape");
+  MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
+  MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)dW & 15) == 0), "CD dW must be 16-byte aligned");
+  MH_CUDA_OK(cudaMemsetAsync(flag_ws, 0, sizeof(int) * (size_t)(C_pad / BM), (cudaStream_t)stream));
+  TcArgs a{};
+  a.out = dW; a.raw_dw = 0; a.layout = layout; a.ld = ld;
+  a.w_hat = (const __nv_bfloat16*)w_hat_bf16; a.inv_norm = inv_norm; a.gscal = gscal;
+  a.rsum = nullptr; a.rsum_parts = 0; a.rpart = rpart_ws; a.rflag = flag_ws;
+  if (int e = make_tmap(&a.tmW, w_hat_bf16, C_pad, MH_D, BM)) return e;
   return launch_dw(G_bf16, B_pad, C, C_pad, x_hat_bf16, a, (cudaStream_t)stream);
 }

@@ -61,6 +61,11 @@ def _on_device_of(argpos: int, same_device=(0, 1, 2, 3)):
     return deco
 
 
+def _selfproj() -> bool:
+    """MH_DW_SELFPROJ=1 selects the self-projecting dW kernel (mh_tc_backward_dw_proj) and a dx GEMM without side pass."""
+    return os.environ.get("MH_DW_SELFPROJ", "0") == "1"
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -221,14 +226,24 @@ class HeadEngine:
         w_hat = self._buf("w_hat", (C_pad, L.D), torch.bfloat16, dev)
         inv_norm = self._buf("inv_norm", (Cn,), torch.float32, dev)
         w_hat32 = self._buf("w_hat32", (Cn, L.D), torch.float32, dev) if exact else None
+        run_pw = True
         if self._shadow_once and not exact and self._shadow == (W.data_ptr(), W._version, w_hat.data_ptr()):
             self._shadow = None         # prefetch_w ran the prologue of THIS forward; the next one runs its own
             self._shadow_once = False
+            run_pw = False
         elif exact or self._shadow != (W.data_ptr(), W._version, w_hat.data_ptr()):
             self._shadow = None
             self._shadow_once = False
+        else:
+            run_pw = False              # sgd_step() wrote w_hat / inv_norm from this very W (same storage, same version)
+
+        # ---- one C call for the whole forward (single GPU, tensor-core path): see csrc/step.cu -------------------------
+        plus = self.family in ("elastic_cos", "elastic_arc") and bool(self.cfg.plus)
+        if (not exact and self.shard.world == 1 and self.family != "vpl_arcface" and not plus
+                and os.environ.get("MH_STEP_API", "1") != "0"):
+            return self._forward_step(x, W, labels, state, margins, update_state, want_grad, run_pw, B, B_pad, C_pad, ld)
+        if run_pw:
             L.call("mh_prologue_w", _ptr(W), self.layout, Cn, ld, _ptr(w_hat), C_pad, _ptr(w_hat32), _ptr(inv_norm), st)
-        # else: sgd_step() wrote w_hat / inv_norm from this very W (same storage, same version counter)
 
         x_hat = self._buf("x_hat", (B_pad, L.D), torch.bfloat16, dev)
         x_hat32 = self._buf("x_hat32", (B, L.D), torch.float32, dev)
@@ -308,6 +323,67 @@ class HeadEngine:
                     scalars=scalars, S=S, pre=pre, logits=logits, exact=exact, gen=self._gen, state=state,
                     W_shape=tuple(W.shape), ld=ld, stash=stash, w_gemm=w_gemm, vpl_alpha=alpha)
 
+    def _forward_step(self, x, W, labels, state, margins, update_state, want_grad, run_pw, B, B_pad, C_pad, ld):
+        """The forward through mh_step_forward: same kernels, same workspaces, one FFI call (host overhead of the
+        launch-bound configs).  The descriptor is rebuilt only when a shape, dtype or workspace pointer changes."""
+        dev = x.device
+        Cn = self.C
+        lib = L.load()
+        n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
+        stash = bool(want_grad and self.stash_ok())
+        b = self._buf
+        T = dict(
+            w_hat=b("w_hat", (C_pad, L.D), torch.bfloat16, dev), inv_norm=b("inv_norm", (Cn,), torch.float32, dev),
+            x_hat=b("x_hat", (B_pad, L.D), torch.bfloat16, dev), x_hat32=b("x_hat32", (B, L.D), torch.float32, dev),
+            xnorm=b("xnorm", (B,), torch.float32, dev), t_raw=b("t_raw", (B,), torch.float32, dev),
+            label_local=b("label_local", (B_pad,), torch.int32, dev), rowp=b("rowp", (L.RP_PLANES, B_pad), torch.float32, dev),
+            stats_tiles=b("stats_tiles", (n_tiles, L.ST_PLANES, B_pad), torch.float32, dev),
+            merge_scratch=b("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev),
+            stats=b("stats", (L.ST_PLANES, B_pad), torch.float32, dev), rowout=b("rowout", (L.RO_PLANES, B_pad), torch.float32, dev))
+        part_splits = 0
+        if want_grad:
+            key = (B_pad, C_pad)
+            if getattr(self, "_nsplit_key", None) != key:
+                ns = C.c_int(0)
+                L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), _ptr(None), _stream())
+                self._nsplit_key, self._nsplit = key, ns.value
+            part_splits = self._nsplit
+            T.update(bc=b("G", (B_pad, C_pad), torch.bfloat16, dev),
+                     dxhat_part=b("dxhat_part", (part_splits, B_pad, L.D), torch.float32, dev),
+                     gscal=b("gscal", (2,), torch.float32, dev), dx_sync=b("dx_sync", (L.DX_SYNC_INTS,), torch.int32, dev))
+            if _selfproj():
+                T.update(rpart=b("dw_rpart", (4, C_pad), torch.float32, dev),
+                         rflag=b("dw_rflag", (C_pad // L.TILE,), torch.int32, dev))
+            else:
+                T.update(r_colsum=b("r_colsum", (B_pad // L.TILE if stash else 1, C_pad), torch.float32, dev))
+            if stash:
+                T.update(xs=b("xs", (B_pad, L.D), torch.bfloat16, dev), rho=b("rho", (B_pad,), torch.float32, dev),
+                         gty=b("gty", (B_pad,), torch.float32, dev),
+                         dxhat_full=b("dxhat_full", (1, B_pad, L.D), torch.float32, dev))
+        sig = (B, B_pad, Cn, C_pad, ld, self.layout, x.dtype, tuple((k, t.data_ptr()) for k, t in T.items()))
+        if getattr(self, "_step_sig", None) != sig:
+            ws = L.MhStepWs()
+            ws.B, ws.B_pad, ws.C, ws.C_pad, ws.ld = B, B_pad, Cn, C_pad, ld
+            ws.layout, ws.x_dtype = self.layout, _DT[x.dtype]
+            ws.n_tiles, ws.part_splits = n_tiles, part_splits
+            for k, t in T.items():
+                setattr(ws, k, t.data_ptr())
+            self._step_sig, self._step_ws = sig, ws
+        ws = self._step_ws
+        if self.family in ("elastic_cos", "elastic_arc"):
+            assert margins is not None and margins.numel() == B
+            margins = margins.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            margins = None
+        scalars = torch.empty(4, dtype=torch.float32, device=dev)      # loss, acc@1, acc@5, loss_g (fresh: returned to the user)
+        L.call("mh_step_forward", C.byref(self.cfg), C.byref(ws), _ptr(x), _ptr(labels), _ptr(W), _ptr(margins), _ptr(state),
+               1 if update_state else 0, 1 if run_pw else 0, 1 if stash else 0, _ptr(scalars), _stream())
+        return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=T["w_hat"], w_hat32=None, inv_norm=T["inv_norm"],
+                    x_hat=T["x_hat"], x_hat32=T["x_hat32"], xnorm=T["xnorm"], label_local=T["label_local"], rowp=T["rowp"],
+                    rowout=T["rowout"], scalars=scalars, S=None, pre=None, logits=None, exact=False, gen=self._gen,
+                    state=state, W_shape=tuple(W.shape), ld=ld, stash=T.get("bc") if stash else None, w_gemm=T["w_hat"],
+                    vpl_alpha=None, step_ws=ws if want_grad else None, step_stash=stash, margins=margins)
+
     # -- backward of the fused loss ------------------------------------------------------------------
     @_on_device_of(0)
     def backward(self, ctx: Dict, g_loss: torch.Tensor, g_lossg: Optional[torch.Tensor],
@@ -319,6 +395,17 @@ class HeadEngine:
         dev = ctx["x_hat"].device
         B, B_pad, C_pad, Cn = ctx["B"], ctx["B_pad"], ctx["C_pad"], self.C
         st = _stream()
+        if ctx.get("step_ws") is not None:
+            # one C call for the whole backward (csrc/step.cu); the forward of this step built the descriptor
+            if g_loss is not None and g_loss.dtype != torch.float32:
+                g_loss = g_loss.float()
+            if g_lossg is not None and g_lossg.dtype != torch.float32:
+                g_lossg = g_lossg.float()
+            dx = torch.empty((B, L.D), dtype=ctx["x_dtype"], device=dev) if need_dx else None
+            dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev) if need_dw else None
+            L.call("mh_step_backward", C.byref(self.cfg), C.byref(ctx["step_ws"]), 1 if ctx["step_stash"] else 0,
+                   _ptr(ctx["state"]), _ptr(g_loss), _ptr(g_lossg), _ptr(dx), _ptr(dW), st)
+            return dx, dW
         gscal = self._gscal(g_loss, g_lossg, B, dev)
         rowp, rowout, state = ctx["rowp"], ctx["rowout"], ctx["state"]
         lse2 = rowout[L.RO["LSE2"]]
@@ -331,25 +418,32 @@ class HeadEngine:
         stash = ctx.get("stash")
         if self.family == "vpl_arcface":
             return self._backward_vpl(ctx, gscal, need_dx, need_dw)
+        # dW projection r_j = w^_j . dw^_j: produced beforehand by the dx side pass / the backward-G column sums (default),
+        # or (MH_DW_SELFPROJ=1) taken from the dW accumulators themselves - measured break-even, see DESIGN.md 4.2
+        selfp = _selfproj()
         r_parts = B_pad // L.TILE if stash is not None else 1      # stash: one partial per 128-row block (no atomics)
-        rsum = self._buf("r_colsum", (r_parts, C_pad), torch.float32, dev)
+        rsum = None if selfp else self._buf("r_colsum", (r_parts, C_pad), torch.float32, dev)
         ns = C.c_int(0)
-        L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), st)
+        L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), _ptr(None), st)
         n_split = ns.value
         split_stride = B_pad * L.D
+        dxsync = self._buf("dx_sync", (L.DX_SYNC_INTS,), torch.int32, dev)
         dx = dW = None
         if stash is not None:
             # stash mode: G_ij = rho_i E'_ij off the target column; the target column is a sparse fp32 term.
-            # The dx GEMM always runs: its idle epilogue warps also produce r_colsum for the dW projection.
             G = stash
             xs = self._buf("xs", (B_pad, L.D), torch.bfloat16, dev)
             rho = self._buf("rho", (B_pad,), torch.float32, dev)
             gty = self._buf("gty", (B_pad,), torch.float32, dev)
             L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
                    _ptr(xs), _ptr(rho), _ptr(gty), st)
-            part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
-            L.call("mh_tc_backward_dx_stash", C.byref(self.cfg), _ptr(G), B_pad, Cn, C_pad, _ptr(w_hat), _ptr(rho), _ptr(rowp),
-                   B_pad, _ptr(part), _ptr(rsum), C.byref(ns), st)
+            if need_dx or not selfp:       # without self-projection the dx kernel's side pass also produces r_colsum
+                part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
+                if selfp:
+                    L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(w_hat), _ptr(part), C.byref(ns), _ptr(dxsync), st)
+                else:
+                    L.call("mh_tc_backward_dx_stash", C.byref(self.cfg), _ptr(G), B_pad, Cn, C_pad, _ptr(w_hat), _ptr(rho),
+                           _ptr(rowp), B_pad, _ptr(part), _ptr(rsum), C.byref(ns), _ptr(dxsync), st)
             if need_dx:
                 full = self._buf("dxhat_full", (1, B_pad, L.D), torch.float32, dev)
                 L.call("mh_stash_dx_combine", _ptr(part), n_split, split_stride, _ptr(rho), _ptr(gty), _ptr(label_local),
@@ -358,16 +452,23 @@ class HeadEngine:
         else:
             G = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
             L.call("mh_tc_backward_g", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_hat), Cn, C_pad,
-                   _ptr(rowp), B_pad, _ptr(label_local), _ptr(state), _ptr(lse2), _ptr(G), _ptr(rsum if need_dw else None), st)
+                   _ptr(rowp), B_pad, _ptr(label_local), _ptr(state), _ptr(lse2), _ptr(G),
+                   _ptr(rsum if (need_dw and not selfp) else None), st)
             xs = x_hat
             if need_dx:
                 part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
-                L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(w_hat), _ptr(part), C.byref(ns), st)
+                L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(w_hat), _ptr(part), C.byref(ns), _ptr(dxsync), st)
                 dx = self._finish_dx(ctx, part, n_split, split_stride, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
         if need_dw:
             dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
-            L.call("mh_tc_backward_dw_fused", _ptr(G), B_pad, Cn, C_pad, _ptr(xs), _ptr(w_hat), _ptr(ctx["inv_norm"]),
-                   _ptr(rsum), r_parts, _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], st)
+            if selfp:
+                rpart = self._buf("dw_rpart", (4, C_pad), torch.float32, dev)
+                rflag = self._buf("dw_rflag", (C_pad // L.TILE,), torch.int32, dev)
+                L.call("mh_tc_backward_dw_proj", _ptr(G), B_pad, Cn, C_pad, _ptr(xs), _ptr(w_hat), _ptr(ctx["inv_norm"]),
+                       _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], _ptr(rpart), _ptr(rflag), st)
+            else:
+                L.call("mh_tc_backward_dw_fused", _ptr(G), B_pad, Cn, C_pad, _ptr(xs), _ptr(w_hat), _ptr(ctx["inv_norm"]),
+                       _ptr(rsum), r_parts, _ptr(gscal), self.layout, _ptr(dW), ctx["ld"], st)
             if stash is not None:
                 L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
                        _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
@@ -391,9 +492,9 @@ class HeadEngine:
         dx = dW = None
         if need_dx:
             ns = C.c_int(0)
-            L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), st)
+            L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), _ptr(None), st)
             part = self._buf("dxhat_part", (ns.value, B_pad, L.D), torch.float32, dev)
-            L.call("mh_tc_backward_dx", _ptr(stash), B_pad, C_pad, _ptr(ctx["w_gemm"]), _ptr(part), C.byref(ns), st)
+            L.call("mh_tc_backward_dx", _ptr(stash), B_pad, C_pad, _ptr(ctx["w_gemm"]), _ptr(part), C.byref(ns), _ptr(None), st)
             full = self._buf("dxhat_full", (1, B_pad, L.D), torch.float32, dev)
             # gty already carries (1 - a_y): the target column reaches x^ through w^_y only
             L.call("mh_stash_dx_combine", _ptr(part), ns.value, B_pad * L.D, _ptr(rho), _ptr(gty), _ptr(label_local),

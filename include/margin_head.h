@@ -200,9 +200,12 @@ int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t 
 
 /* dx_hat partials = G . w_hat, split over the class dimension.
  * Returns the number of splits through *n_split_host (call with out == NULL to query).
- * out is [n_split, B_pad, 512] fp32. */
+ * out is [n_split, B_pad, 512] fp32.  sync_ws (may be NULL): MH_DX_SYNC_INTS ints of caller-owned scratch; when given
+ * and every tile of the launch is resident at once, the CTAs that stream the same w^ k-blocks (one split, all row
+ * tiles) rendezvous every 16 k-blocks so that w^ is fetched from HBM once per split, not once per row tile. */
+#define MH_DX_SYNC_INTS 64
 int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* w_hat_bf16,
-                      float* out, int* n_split_host, void* stream);
+                      float* out, int* n_split_host, int* sync_ws, void* stream);
 
 /* Stash mode: the same GEMM on the stash E' (out = E' . w_hat; scale the rows by rho afterwards, mh_stash_dx_combine).
  * While the tensor cores run, the kernel's idle epilogue warps re-read every E' tile from shared memory and store
@@ -214,7 +217,7 @@ int mh_tc_backward_dx(const void* G_bf16, int64_t B_pad, int64_t C_pad, const vo
  * cases occupy disjoint ranges of log2(E') for a given row threshold (rowp plane MH_RP_THR), so cos is recovered exactly. */
 int mh_tc_backward_dx_stash(const mh_config* cfg_host, const void* stash_bf16, int64_t B_pad, int64_t C, int64_t C_pad,
                             const void* w_hat_bf16, const float* rho, const float* rowp, int64_t ldp, float* out,
-                            float* r_colsum, int* n_split_host, void* stream);
+                            float* r_colsum, int* n_split_host, int* sync_ws, void* stream);
 
 /* dw_hat = G^T . x_hat, [C_pad, 512] fp32 (unscaled, unprojected). */
 int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const void* x_hat_bf16,
@@ -228,6 +231,14 @@ int mh_tc_backward_dw(const void* G_bf16, int64_t B_pad, int64_t C_pad, const vo
 int mh_tc_backward_dw_fused(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
                             const void* w_hat_bf16, const float* inv_norm, const float* r_colsum, int r_parts,
                             const float* gscal, int layout, float* dW, int64_t ld, void* stream);
+
+/* dW with the projection term taken from the accumulators: r_j = w^_j . dw^_j is formed inside the kernel (the two
+ * CTA pairs holding the two d halves of a class tile exchange four partial dots per class through rpart_ws, summed in a
+ * fixed order: bit-reproducible, no atomics on data), so no r_colsum input and no side pass in the dx kernel.
+ * rpart_ws: [4 * C_pad] floats, flag_ws: [C_pad / 128] ints - caller-owned scratch (flag_ws is zeroed here). */
+int mh_tc_backward_dw_proj(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* x_hat_bf16,
+                           const void* w_hat_bf16, const float* inv_norm, const float* gscal, int layout,
+                           float* dW, int64_t ld, float* rpart_ws, int* flag_ws, void* stream);
 
 /* ---- stash backward: O(B*d) helpers (see mh_tc_forward's stash) -------------------------------------- */
 
@@ -308,6 +319,61 @@ int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, const float*
 
 /* gscal[0] = upstream_grad(loss_id) / B_total, gscal[1] = upstream_grad(loss_g): device floats so
  * that a GradScaler-scaled backward (model_utils.py:185) needs no host sync. */
+
+/* ---- whole-phase entry points (single GPU, tensor-core path) -------------------------------------------------- */
+
+/* Workspace descriptor shared by mh_step_forward / mh_step_backward: every pointer is a caller-owned DEVICE buffer with
+ * the shape given in DESIGN.md section 3 (the same buffers the per-kernel entry points take). */
+typedef struct mh_step_ws {
+  int64_t B, B_pad, C, C_pad;  /* B_pad, C_pad: multiples of 256 */
+  int64_t ld;                  /* row pitch of W and dW in elements (512 for [C,D], C for [D,C]) */
+  int32_t layout;              /* mh_layout of W / dW */
+  int32_t x_dtype;             /* mh_dtype of x and dx */
+  void* w_hat;                 /* bf16 [C_pad, 512] */
+  float* inv_norm;             /* [C] */
+  void* x_hat;                 /* bf16 [B_pad, 512] */
+  float* x_hat32;              /* [B, 512] */
+  float* xnorm;                /* [B] */
+  float* t_raw;                /* [B] */
+  int32_t* label_local;        /* [B_pad] */
+  float* rowp;                 /* [MH_RP_PLANES, B_pad] */
+  float* stats_tiles;          /* [n_tiles, MH_ST_PLANES, B_pad] */
+  int64_t n_tiles;             /* = mh_fwd_num_tiles(C_pad) */
+  float* merge_scratch;        /* [MH_MERGE_BLOCKS, MH_ST_PLANES, B_pad] */
+  float* stats;                /* [MH_ST_PLANES, B_pad] */
+  float* rowout;               /* [MH_RO_PLANES, B_pad] */
+  void* bc;                    /* bf16 [B_pad, C_pad] class-tiled: the stash or G (NULL: forward-only use) */
+  void* xs;                    /* bf16 [B_pad, 512] (stash mode) */
+  float* rho;                  /* [B_pad] (stash mode) */
+  float* gty;                  /* [B_pad] (stash mode) */
+  float* dxhat_part;           /* [part_splits, B_pad, 512] */
+  int64_t part_splits;         /* >= the split count mh_tc_backward_dx reports for (B_pad, C_pad) */
+  float* dxhat_full;           /* [B_pad, 512] (stash mode) */
+  float* gscal;                /* [2] */
+  float* r_colsum;             /* [B_pad / 128, C_pad]: projection partials from the dx side pass / backward-G sums; NULL selects
+                                  the self-projecting dW kernel (mh_tc_backward_dw_proj), which needs the next two instead */
+  float* rpart;                /* [4, C_pad] or NULL */
+  int32_t* rflag;              /* [C_pad / 128] or NULL */
+  int32_t* dx_sync;            /* [MH_DX_SYNC_INTS] or NULL */
+} mh_step_ws;
+
+/* Forward of one step: mh_prologue_w (skipped when run_prologue_w == 0: w_hat / inv_norm already hold this W, e.g.
+ * after mh_sgd_step_w), mh_prologue_x, mh_row_params, mh_tc_forward (stashing into ws->bc when stash != 0; needs
+ * mh_tc_stash_ok), mh_merge_stats, mh_finalize_rows.  scalars[4] = {mean CE loss, acc@1 %, acc@5 %, loss_g}.
+ * Replaces the head forward + nn.CrossEntropyLoss + accuracy of model_utils.py:177-182 in ONE host call. */
+int mh_step_forward(const mh_config* cfg_host, const mh_step_ws* ws, const void* x, const int64_t* labels,
+                    const float* W, const float* margins, float* state, int update_state, int run_prologue_w,
+                    int stash, float* scalars, void* stream);
+
+/* Backward of the step whose forward just ran on the same workspace (stash must match): mh_make_gscal, then either the
+ * stash backward (mh_stash_prep, mh_tc_backward_dx_stash, mh_stash_dx_combine, mh_norm_backward_x,
+ * mh_tc_backward_dw_fused, mh_stash_dw_target) or the recompute backward (mh_tc_backward_g, mh_tc_backward_dx,
+ * mh_norm_backward_x, mh_tc_backward_dw_fused); with ws->r_colsum == NULL the dW kernel is mh_tc_backward_dw_proj
+ * and the dx GEMM runs without its side pass.  g_loss / g_lossg: device scalars (upstream gradients of loss / loss_g; NULL = 0).
+ * dx ([B, 512] in x_dtype) and dW (parameter layout, fp32) may each be NULL to skip that gradient.
+ * Replaces autograd's backward of model_utils.py:185 through the head in ONE host call. */
+int mh_step_backward(const mh_config* cfg_host, const mh_step_ws* ws, int stash, const float* state,
+                     const float* g_loss, const float* g_lossg, void* dx, float* dW, void* stream);
 
 /* ---- VPL-ArcFace (criterion.py:619-762) ------------------------------------------------------------------ */
 

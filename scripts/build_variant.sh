@@ -6,7 +6,7 @@ set -e
 name=$1; shift
 src=$(cd "$(dirname "$0")/../face_recognition_models_b200/csrc" && pwd)
 out=/tmp/mh_variant_$name; mkdir -p $out
-for f in capi prologue dense stash verify tc_head; do
+for f in capi prologue dense stash verify tc_head step; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c $src/$f.cu -o $out/$f.o 2>/dev/null &
 done
 wait

@@ -161,9 +161,9 @@ def stage_tcgemm():
         Gl = G                                                       # logical [B_pad, C_pad]
         G = G.view(B_pad, C_pad // 128, 128).permute(1, 0, 2).contiguous()   # class-tiled storage the kernels expect
         ns = C.c_int(0)
-        L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(wh), C.c_void_p(0), C.byref(ns), _stream())
+        L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(wh), C.c_void_p(0), C.byref(ns), C.c_void_p(0), _stream())
         part = torch.zeros(ns.value, B_pad, 512, device=dev)
-        L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(wh), _ptr(part), C.byref(ns), _stream())
+        L.call("mh_tc_backward_dx", _ptr(G), B_pad, C_pad, _ptr(wh), _ptr(part), C.byref(ns), C.c_void_p(0), _stream())
         torch.cuda.synchronize()
         got = part.sum(0)
         ref = Gl.double() @ wh.double()

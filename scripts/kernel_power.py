@@ -125,7 +125,7 @@ def replay(tag, name, args):
 
 
 BIG = ("mh_prologue_w", "mh_tc_forward", "mh_tc_backward_g", "mh_tc_backward_dx", "mh_tc_backward_dx_stash",
-       "mh_tc_backward_dw_fused", "mh_tc_backward_dw")
+       "mh_tc_backward_dw_fused", "mh_tc_backward_dw", "mh_tc_backward_dw_proj")
 for tag, mode, grad in (("stash", "auto", True), ("recompute", "recompute", True), ("nograd", "auto", False)):
     if ONLY and tag not in ONLY:
         continue

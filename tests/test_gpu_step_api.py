@@ -1,0 +1,62 @@
+"""GPU: the whole-phase entry points (mh_step_forward / mh_step_backward, csrc/step.cu) run the same kernels as the
+entry-point-by-entry-point driver, so the results must be bit-identical; the self-projecting dW kernel
+(MH_DW_SELFPROJ=1, mh_tc_backward_dw_proj) must meet the same parity bar against the oracle and be bit-reproducible."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fam, bmode, B, Cn, seed=21):
+    import face_recognition_models_b200 as pkg
+    from oracle import margin_oracle as mo
+    from tests.helpers import build_head, prime_head
+    cfg = mo.HeadConfig.default(fam)
+    x, W, labels = mo.make_inputs(fam, B, Cn, 512, seed=seed)
+    margins = None
+    if fam.startswith("elastic"):
+        torch.manual_seed(99)
+        margins = mo.sample_elastic_margins(cfg, B)
+    head = prime_head(build_head(pkg, fam, cfg, Cn).cuda(), fam, W, mo.HeadState(), margins)
+    head.backward_mode = bmode
+    xg = x.cuda().requires_grad_(True)
+    out = head.fused_loss(xg, labels.cuda())
+    (out.loss + 0.5 * out.loss_g).backward()
+    torch.cuda.synchronize()
+    return (out.loss.detach().clone(), out.acc1.clone(), out.acc5.clone(), xg.grad.clone(), head._param().grad.clone(),
+            (cfg, x, W, labels, margins))
+
+
+@pytest.mark.parametrize("fam,bmode", [("arcface", "auto"), ("arcface", "recompute"), ("cosface", "auto"),
+                                       ("curricularface", "auto"), ("sphereface", "auto"), ("magface", "auto"),
+                                       ("mv_am", "auto"), ("elastic_arc", "auto"), ("adaface", "auto")])
+def test_step_api_is_bit_identical_to_the_per_kernel_driver(fam, bmode, monkeypatch):
+    monkeypatch.setenv("MH_STEP_API", "1")
+    a = _run(fam, bmode, 300, 4097)
+    monkeypatch.setenv("MH_STEP_API", "0")
+    b = _run(fam, bmode, 300, 4097)
+    for u, v in zip(a[:5], b[:5]):
+        assert torch.equal(u, v), fam
+
+
+@pytest.mark.parametrize("fam,bmode", [("arcface", "auto"), ("arcface", "recompute"), ("cosface", "auto"),
+                                       ("curricularface", "auto"), ("mv_am", "auto")])
+@pytest.mark.parametrize("step_api", ["1", "0"])
+def test_self_projecting_dw_matches_oracle(fam, bmode, step_api, monkeypatch):
+    from oracle import margin_oracle as mo
+    from tests.helpers import cosim, rel
+    monkeypatch.setenv("MH_DW_SELFPROJ", "1")
+    monkeypatch.setenv("MH_STEP_API", step_api)
+    B, Cn = 300, 70_001                         # 274 class tiles: every CTA pair exchanges partials over several tiles
+    loss, a1, a5, dx, dW, (cfg, x, W, labels, margins) = _run(fam, bmode, B, Cn)
+    ref = mo.loss_and_grads(cfg, mo.HeadState(), x, W, labels, margins=margins, lambda_g=0.5)
+    assert abs(float(loss) - float(ref["loss_id"])) < 2e-3 * abs(float(ref["loss_id"]))
+    assert cosim(dx, ref["dx"]) > 0.9995 and cosim(dW, ref["dW"]) > 0.9995
+    assert rel(dW, ref["dW"]) < 1e-2
+    # bit-reproducible in BOTH backward modes (fixed-order sum of four partial dots, no atomics)
+    again = _run(fam, bmode, B, Cn)
+    assert torch.equal(dW, again[4]) and torch.equal(dx, again[3])
+    # and consistent with the default projection path
+    monkeypatch.setenv("MH_DW_SELFPROJ", "0")
+    base = _run(fam, bmode, B, Cn)
+    assert rel(dW, base[4]) < 2e-3 and torch.equal(dx, base[3])

@@ -606,10 +606,24 @@ def run_b200(args):
         loss_val = float(out.loss.detach())
         if sampler:
             sampler.active = True
-        # ---- device-resident arm, with per-kernel CUDA events on the launching stream ----------------------
-        L.PROFILE = []
+        # ---- device-resident arm -----------------------------------------------------------------------------------
         ms = timed(step_resident, args.steps)
+        # ---- the same K steps again with CUDA events around every C-ABI entry point on the launching stream (the
+        # product path issues a step as two calls, mh_step_forward / mh_step_backward; MH_STEP_API=0 drives the same
+        # kernels one entry point at a time so that each can be timed): feeds `kernels` and `roofline`, not `value`
+        prev_api = os.environ.get("MH_STEP_API")
+        os.environ["MH_STEP_API"] = "0"
+        for _ in range(2):
+            step_resident()
+        L.PROFILE = []
+        timed(step_resident, args.steps)
         prof, L.PROFILE = L.PROFILE, None
+        if prev_api is None:
+            os.environ.pop("MH_STEP_API", None)
+        else:
+            os.environ["MH_STEP_API"] = prev_api
+        for _ in range(2):
+            step_resident()
         # ---- the other backward mode (recompute: north_star's "backward recomputes logit tiles"), same protocol ----
         ms_alt = None
         stash = eng.stash_ok()
@@ -635,7 +649,7 @@ def run_b200(args):
             k[0] += e0.elapsed_time(e1)
             k[1] += 1 if launches else 0
             k[2] += launches
-        n_launch += sum(k[2] for k in kern.values())
+        n_launch += sum(k[2] for k in kern.values())      # launches of one K-step pass (same kernels in both drivers)
         kern_all[fam] = kern
         tot_ms += ms
         tot_ms_e2e += ms_e2e

@@ -71,6 +71,7 @@ def _round_up(a: int, b: int) -> int:
 
 
 _DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}
+_DEVICE_OK = set()
 
 
 def sphere_lambda(it: int) -> float:
@@ -113,6 +114,9 @@ class HeadEngine:
         self._shadow = None             # (W.data_ptr(), W._version, w_hat.data_ptr()) when sgd_step left a valid w_hat behind
         self._shadow_once = False       # set by prefetch_w: good for the next forward only (never a cross-step cache)
         self.vpl = None                 # VPLArcFace: dict(mem, life, lamda) set by the head before each forward
+        self._step_key = None           # cached mh_step_ws descriptor of the whole-phase entry points (see _forward_step)
+        self._step_ws = self._step_T = None
+        self._stash_ok_key = None
         # "auto" | "stash" | "recompute"; MH_BACKWARD in the environment overrides (A/B measurements)
         self.backward_mode = os.environ.get("MH_BACKWARD", "auto")
 
@@ -138,6 +142,15 @@ class HeadEngine:
     def release_workspaces(self):
         self._ws.clear()
         self._shadow = None
+        self._step_key = self._step_ws = self._step_T = None
+
+    def _stash_ok_cached(self) -> bool:
+        """stash_ok() depends only on the hyper-parameters, the shard size and backward_mode: asked once per change."""
+        key = (self.backward_mode, self.mode, self.family, float(self.cfg.s), float(self.cfg.mv_weight), self.C)
+        if self._stash_ok_key != key:
+            self._stash_ok_val = self.stash_ok()
+            self._stash_ok_key = key
+        return self._stash_ok_val
 
     def invalidate_shadow(self):
         """Forget the w_hat left by sgd_step().  Only needed after writing the parameter behind autograd's back
@@ -194,16 +207,22 @@ class HeadEngine:
     @_on_device_of(0)
     def forward(self, x: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, state: torch.Tensor,
                 margins: Optional[torch.Tensor], update_state: bool = True, want_dense: bool = False,
-                want_grad: bool = False):
+                want_grad: bool = False, t_ext: Optional[torch.Tensor] = None):
         """Runs prologues + fused forward.  x is the (already gathered) global batch [B, 512].
         want_grad: a backward will follow, so the forward may stash E' (see the module docstring).
+
+        t_ext: externally computed target cosines [B] (QAFace: the target column is x^ . normalise(w_y + injection),
+        criterion.py:1487-1490, formed differentiably by the caller); they replace the prologue's <x^, w^_y> and the
+        backward hands d loss / d t_ext back instead of applying the target column to dx / dW.
 
         Returns a context dict with every tensor the backward needs plus the user-visible outputs.
         """
         lib = L.load()
         if not x.is_cuda:
             raise L.MarginHeadError("margin head inputs must be CUDA tensors (no CPU fallback)")
-        L.check(lib.mh_device_check(), "mh_device_check")
+        if x.device.index not in _DEVICE_OK:
+            L.check(lib.mh_device_check(), "mh_device_check")        # once per device: compute capability 10.x
+            _DEVICE_OK.add(x.device.index)
         assert x.dim() == 2 and x.shape[1] == L.D, "embedding dimension must be 512"
         assert x.dtype in _DT, x.dtype
         assert W.dtype == torch.float32 and W.is_contiguous()
@@ -256,6 +275,10 @@ class HeadEngine:
         if self.shard.world > 1:
             # every rank needs every row's target cosine (thresholds, EMA); only the owner computed it
             self.shard.comm.allreduce_sum_(t_raw)
+        if t_ext is not None:
+            if self.family != "vpl_arcface" or self.shard.world > 1:
+                raise L.MarginHeadError("external target cosines are supported by the memory-bank heads on one GPU only")
+            t_raw.copy_(t_ext.detach().to(torch.float32))
 
         w_gemm = w_hat
         alpha = None
@@ -271,7 +294,8 @@ class HeadEngine:
                        Cn, C_pad, _ptr(w_gemm), _ptr(alpha), st)
             else:
                 alpha.zero_()
-            margins = alpha[labels].contiguous()
+            # the row's interpolation weight of the target column; an external target cosine is already final
+            margins = alpha[labels].contiguous() if t_ext is None else torch.zeros(B, dtype=torch.float32, device=dev)
         elif self.family in ("elastic_cos", "elastic_arc"):
             assert margins is not None and margins.numel() == B
             margins = margins.to(device=dev, dtype=torch.float32).contiguous()
@@ -321,54 +345,55 @@ class HeadEngine:
         return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=w_hat, w_hat32=w_hat32, inv_norm=inv_norm,
                     x_hat=x_hat, x_hat32=x_hat32, xnorm=xnorm, label_local=label_local, rowp=rowp, rowout=rowout,
                     scalars=scalars, S=S, pre=pre, logits=logits, exact=exact, gen=self._gen, state=state,
-                    W_shape=tuple(W.shape), ld=ld, stash=stash, w_gemm=w_gemm, vpl_alpha=alpha)
+                    W_shape=tuple(W.shape), ld=ld, stash=stash, w_gemm=w_gemm, vpl_alpha=alpha, t_ext=t_ext is not None)
 
     def _forward_step(self, x, W, labels, state, margins, update_state, want_grad, run_pw, B, B_pad, C_pad, ld):
         """The forward through mh_step_forward: same kernels, same workspaces, one FFI call (host overhead of the
         launch-bound configs).  The descriptor is rebuilt only when a shape, dtype or workspace pointer changes."""
         dev = x.device
         Cn = self.C
-        lib = L.load()
-        n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
-        stash = bool(want_grad and self.stash_ok())
-        b = self._buf
-        T = dict(
-            w_hat=b("w_hat", (C_pad, L.D), torch.bfloat16, dev), inv_norm=b("inv_norm", (Cn,), torch.float32, dev),
-            x_hat=b("x_hat", (B_pad, L.D), torch.bfloat16, dev), x_hat32=b("x_hat32", (B, L.D), torch.float32, dev),
-            xnorm=b("xnorm", (B,), torch.float32, dev), t_raw=b("t_raw", (B,), torch.float32, dev),
-            label_local=b("label_local", (B_pad,), torch.int32, dev), rowp=b("rowp", (L.RP_PLANES, B_pad), torch.float32, dev),
-            stats_tiles=b("stats_tiles", (n_tiles, L.ST_PLANES, B_pad), torch.float32, dev),
-            merge_scratch=b("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev),
-            stats=b("stats", (L.ST_PLANES, B_pad), torch.float32, dev), rowout=b("rowout", (L.RO_PLANES, B_pad), torch.float32, dev))
-        part_splits = 0
-        if want_grad:
-            key = (B_pad, C_pad)
-            if getattr(self, "_nsplit_key", None) != key:
+        stash = bool(want_grad and self._stash_ok_cached())
+        key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj())
+        if self._step_key != key:
+            lib = L.load()
+            n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
+            b = self._buf
+            T = dict(
+                w_hat=b("w_hat", (C_pad, L.D), torch.bfloat16, dev), inv_norm=b("inv_norm", (Cn,), torch.float32, dev),
+                x_hat=b("x_hat", (B_pad, L.D), torch.bfloat16, dev), x_hat32=b("x_hat32", (B, L.D), torch.float32, dev),
+                xnorm=b("xnorm", (B,), torch.float32, dev), t_raw=b("t_raw", (B,), torch.float32, dev),
+                label_local=b("label_local", (B_pad,), torch.int32, dev),
+                rowp=b("rowp", (L.RP_PLANES, B_pad), torch.float32, dev),
+                stats_tiles=b("stats_tiles", (n_tiles, L.ST_PLANES, B_pad), torch.float32, dev),
+                merge_scratch=b("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev),
+                stats=b("stats", (L.ST_PLANES, B_pad), torch.float32, dev),
+                rowout=b("rowout", (L.RO_PLANES, B_pad), torch.float32, dev))
+            part_splits = 0
+            if want_grad:
                 ns = C.c_int(0)
                 L.call("mh_tc_backward_dx", _ptr(None), B_pad, C_pad, _ptr(None), _ptr(None), C.byref(ns), _ptr(None), _stream())
-                self._nsplit_key, self._nsplit = key, ns.value
-            part_splits = self._nsplit
-            T.update(bc=b("G", (B_pad, C_pad), torch.bfloat16, dev),
-                     dxhat_part=b("dxhat_part", (part_splits, B_pad, L.D), torch.float32, dev),
-                     gscal=b("gscal", (2,), torch.float32, dev), dx_sync=b("dx_sync", (L.DX_SYNC_INTS,), torch.int32, dev))
-            if _selfproj():
-                T.update(rpart=b("dw_rpart", (4, C_pad), torch.float32, dev),
-                         rflag=b("dw_rflag", (C_pad // L.TILE,), torch.int32, dev))
-            else:
-                T.update(r_colsum=b("r_colsum", (B_pad // L.TILE if stash else 1, C_pad), torch.float32, dev))
-            if stash:
-                T.update(xs=b("xs", (B_pad, L.D), torch.bfloat16, dev), rho=b("rho", (B_pad,), torch.float32, dev),
-                         gty=b("gty", (B_pad,), torch.float32, dev),
-                         dxhat_full=b("dxhat_full", (1, B_pad, L.D), torch.float32, dev))
-        sig = (B, B_pad, Cn, C_pad, ld, self.layout, x.dtype, tuple((k, t.data_ptr()) for k, t in T.items()))
-        if getattr(self, "_step_sig", None) != sig:
+                part_splits = ns.value
+                T.update(bc=b("G", (B_pad, C_pad), torch.bfloat16, dev),
+                         dxhat_part=b("dxhat_part", (part_splits, B_pad, L.D), torch.float32, dev),
+                         gscal=b("gscal", (2,), torch.float32, dev), dx_sync=b("dx_sync", (L.DX_SYNC_INTS,), torch.int32, dev))
+                if _selfproj():
+                    T.update(rpart=b("dw_rpart", (4, C_pad), torch.float32, dev),
+                             rflag=b("dw_rflag", (C_pad // L.TILE,), torch.int32, dev))
+                else:
+                    T.update(r_colsum=b("r_colsum", (B_pad // L.TILE if stash else 1, C_pad), torch.float32, dev))
+                if stash:
+                    T.update(xs=b("xs", (B_pad, L.D), torch.bfloat16, dev), rho=b("rho", (B_pad,), torch.float32, dev),
+                             gty=b("gty", (B_pad,), torch.float32, dev),
+                             dxhat_full=b("dxhat_full", (1, B_pad, L.D), torch.float32, dev))
             ws = L.MhStepWs()
             ws.B, ws.B_pad, ws.C, ws.C_pad, ws.ld = B, B_pad, Cn, C_pad, ld
             ws.layout, ws.x_dtype = self.layout, _DT[x.dtype]
             ws.n_tiles, ws.part_splits = n_tiles, part_splits
             for k, t in T.items():
                 setattr(ws, k, t.data_ptr())
-            self._step_sig, self._step_ws = sig, ws
+            # the descriptor holds raw pointers: T keeps the tensors alive for as long as the descriptor is cached
+            self._step_key, self._step_ws, self._step_T = key, ws, T
+        T = self._step_T
         ws = self._step_ws
         if self.family in ("elastic_cos", "elastic_arc"):
             assert margins is not None and margins.numel() == B
@@ -489,6 +514,11 @@ class HeadEngine:
         gty = self._buf("gty", (B_pad,), torch.float32, dev)
         L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
                _ptr(xs), _ptr(rho), _ptr(gty), st)
+        ext = bool(ctx.get("t_ext"))
+        # external target cosine (QAFace): the target column does not touch dx / dW here; d loss / d t_i = gscal * gty_i goes
+        # back to the caller's autograd graph instead
+        gty_used = self._buf("gty_zero", (B_pad,), torch.float32, dev, zero=True) if ext else gty
+        ctx["dt_ext"] = (gty[:B] * gscal[0]) if ext else None
         dx = dW = None
         if need_dx:
             ns = C.c_int(0)
@@ -497,7 +527,7 @@ class HeadEngine:
             L.call("mh_tc_backward_dx", _ptr(stash), B_pad, C_pad, _ptr(ctx["w_gemm"]), _ptr(part), C.byref(ns), _ptr(None), st)
             full = self._buf("dxhat_full", (1, B_pad, L.D), torch.float32, dev)
             # gty already carries (1 - a_y): the target column reaches x^ through w^_y only
-            L.call("mh_stash_dx_combine", _ptr(part), ns.value, B_pad * L.D, _ptr(rho), _ptr(gty), _ptr(label_local),
+            L.call("mh_stash_dx_combine", _ptr(part), ns.value, B_pad * L.D, _ptr(rho), _ptr(gty_used), _ptr(label_local),
                    _ptr(w_hat), B, _ptr(full), st)
             dx = self._finish_dx(ctx, full, 1, B_pad * L.D, gscal, rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]])
         if need_dw:
@@ -508,8 +538,9 @@ class HeadEngine:
             torch.sub(1.0, ctx["vpl_alpha"], out=beta)               # 1 - a_j; the normalise-backward is linear in dw^
             L.call("mh_norm_backward_w", _ptr(dwh), _ptr(w_hat), _ptr(None), _ptr(ctx["inv_norm"]), _ptr(gscal), _ptr(beta),
                    Cn, self.layout, _ptr(dW), ctx["ld"], st)
-            L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
-                   _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
+            if not ext:
+                L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
+                       _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
         return dx, dW
 
     def _gscal(self, g_loss, g_lossg, B_total, dev) -> torch.Tensor:
@@ -594,10 +625,11 @@ class FusedMarginLossFn(torch.autograd.Function):
     """loss_id, loss_g, acc1, acc5, norms = f(x, W, labels).  Only loss_id / loss_g are differentiable."""
 
     @staticmethod
-    def forward(ctx, x, W, labels, engine: HeadEngine, state, margins, update_state, grad_enabled=True):
+    def forward(ctx, x, W, labels, engine: HeadEngine, state, margins, update_state, grad_enabled=True, t_ext=None):
         # grad_enabled = torch.is_grad_enabled() at the call site (always False inside Function.forward)
+        needs = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (t_ext is not None and ctx.needs_input_grad[8])
         c = engine.forward(x, W, labels, state, margins, update_state=update_state,
-                           want_grad=bool(grad_enabled and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])))
+                           want_grad=bool(grad_enabled and needs), t_ext=t_ext)
         ctx.engine = engine
         ctx.c = c
         ctx.x_dtype = x.dtype
@@ -613,7 +645,7 @@ class FusedMarginLossFn(torch.autograd.Function):
             g_loss = torch.zeros((), device=ctx.c["x_hat"].device)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx, dW = eng.backward(ctx.c, g_loss, g_lossg, need_dx, need_dw)
-        return dx, dW, None, None, None, None, None, None
+        return dx, dW, None, None, None, None, None, None, ctx.c.get("dt_ext")
 
 
 class DenseMarginLogitsFn(torch.autograd.Function):

@@ -385,8 +385,92 @@ class VPLArcFace(_MarginHeadBase):
                                   "[pre, logits] 4-tuple of criterion.py:762 is not built for this head")
 
 
+class QAFace(_MarginHeadBase):
+    """criterion.py:1331-1520 (QAFace: quality-aware injection memory).
+
+    Same skeleton as VPLArcFace with a BINARY class mask: a class whose memory is alive (``life > 0``) is represented
+    by its normalised memory vector instead of its centre in every non-target column (criterion.py:1480-1484), i.e. the
+    fused GEMM runs on the mixed class vectors of ``mh_vpl_mix`` with lamda = 1.  The target column is
+    ``x^ . normalise(w_y + injection)`` with the RAW centre and the quality-gated, magnitude-normalised ``minput`` row
+    (1459-1461, 1487-1490): an O(B d) term formed here in differentiable PyTorch and handed to the kernels as an external
+    target cosine; the backward returns ``d loss / d t_i``, so gradients reach ``feats``, ``weight`` and ``minput``
+    exactly as the reference's autograd routes them.  The ``muy`` / ``std`` statistics are carried detached between
+    steps (the reference keeps their graph, so its own second backward fails when ``minput`` requires grad).
+    ``fused_loss(feats, minput, labels)`` only: the materialised 4-tuple of criterion.py:1520 is not built.
+    """
+    family, layout, param_name = "vpl_arcface", "CD", "weight"
+
+    def __init__(self, feat_dim: int, num_class: int, s: float = 64.0, m: float = 0.50, easy_margin: bool = True,
+                 delta: int = 1000, tto: float = 2.0, alpha: float = 0.99, device_id=None):
+        super().__init__()
+        if device_id is not None:
+            raise NotImplementedError("device_id model-parallel is replaced by ShardedMarginHead")
+        self.feat_dim, self.num_class, self.s, self.m, self.easy_margin = feat_dim, num_class, s, m, easy_margin
+        self.delta, self.tto, self.alpha, self.device_id = delta, tto, alpha, device_id
+        self.weight = nn.Parameter(torch.empty(num_class, feat_dim))
+        nn.init.xavier_uniform_(self.weight)
+        self.register_buffer("mem", torch.zeros(num_class, feat_dim))
+        self.register_buffer("life", torch.zeros(num_class))
+        self.register_buffer("muy", torch.tensor(0.0))
+        self.register_buffer("std", torch.tensor(1.0))
+        self.register_buffer("cos_m", torch.tensor(math.cos(m), dtype=torch.float32))
+        self.register_buffer("sin_m", torch.tensor(math.sin(m), dtype=torch.float32))
+        self.register_buffer("th", torch.tensor(math.cos(math.pi - m), dtype=torch.float32))
+        self.register_buffer("mm", torch.tensor(math.sin(math.pi - m) * m, dtype=torch.float32))
+        self.norm_training_flag = True
+        self._init_engine(num_class, s=s, m=m, easy_margin=int(bool(easy_margin)))
+
+    def change_training_mode(self, flag: bool):
+        """Toggle quality-aware memory injection (criterion.py:1399-1401)."""
+        self.norm_training_flag = flag
+
+    def injection_cal(self, norm_mag_minput: torch.Tensor) -> torch.Tensor:
+        """exp(-z) where |z| < tto, else 0 (criterion.py:1409-1413)."""
+        f = torch.exp(-norm_mag_minput)
+        return torch.where(torch.abs(norm_mag_minput) < self.tto, f, torch.zeros_like(f))
+
+    def fused_loss(self, feats: torch.Tensor, minput: torch.Tensor, labels: torch.Tensor) -> FusedOutput:
+        self._check(feats, labels)
+        if not self.norm_training_flag:
+            self._engine.vpl = None                                        # plain clamped ArcFace on the class centres
+            out = FusedMarginLossFn.apply(feats, self.weight, labels, self._engine, self._mh_state, None, True,
+                                          torch.is_grad_enabled())
+            return FusedOutput(*out)
+        if minput.shape != feats.shape:
+            raise ValueError("feats / minput shape mismatch")
+        mi = minput.float()
+        mag = torch.norm(mi, p=2, dim=1, keepdim=True)                       # criterion.py:1447
+        mean, sd = mag.mean(), mag.std()
+        first = self.muy == 0.0                                              # 1451: decided on the device, no host sync
+        muy = torch.where(first, mean, self.alpha * self.muy + (1 - self.alpha) * mean)
+        std = torch.where(first, sd, self.alpha * self.std + (1 - self.alpha) * sd)
+        self.muy, self.std = muy.detach(), std.detach()
+        z = ((mag - muy) / (std + 1e-6)).squeeze(1)                          # 1459
+        injection = self.injection_cal(z).unsqueeze(1) * mi / (mag + 1e-6)   # 1460-1461
+        with torch.no_grad():                                                # 1464-1477 without the loop over classes
+            uniq, inv = torch.unique(labels, return_inverse=True)
+            sums = torch.zeros(uniq.numel(), mi.shape[1], dtype=torch.float32, device=mi.device)
+            sums.index_add_(0, inv, injection.detach())
+            cnt = torch.bincount(inv, minlength=uniq.numel()).clamp_min(1).unsqueeze(1)
+            self.mem[uniq] = sums / cnt
+            self.life[uniq] = float(self.delta)
+            self.life.sub_(1.0)
+        xh = torch.nn.functional.normalize(feats.float(), dim=1)
+        tw = torch.nn.functional.normalize(self.weight[labels] + injection, dim=1)     # 1487-1488: raw centre + injection
+        t_ext = (xh * tw).sum(dim=1)                                                    # 1489
+        self._engine.vpl = dict(mem=self.mem, life=self.life, lamda=1.0)               # a_j = 1[life_j > 0]
+        out = FusedMarginLossFn.apply(feats, self.weight, labels, self._engine, self._mh_state, None, True,
+                                      torch.is_grad_enabled(), t_ext)
+        return FusedOutput(*out)
+
+    def forward(self, feats: torch.Tensor, minput: torch.Tensor, labels: torch.Tensor):
+        raise NotImplementedError("QAFace is available through fused_loss(feats, minput, labels); the materialised "
+                                  "[pre, logits] 4-tuple of criterion.py:1520 is not built for this head")
+
+
 HEAD_CLASSES = dict(
     arcface=ArcFace, cosface=CosFace, sphereface=SphereFace, mv_am=MV_Softmax, mv_arc=MV_Softmax,
     curricularface=CurricularFace, adaface=AdaFace, elastic_cos=ElasticCosFace, elastic_arc=ElasticArcFace,
     magface=MagFace, vpl_arcface=VPLArcFace,
 )
+# QAFace takes a second feature tensor (fused_loss(feats, minput, labels)) and is therefore not in HEAD_CLASSES

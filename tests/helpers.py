@@ -12,8 +12,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_files():
-    """Golden vectors of the margin heads (lfw_synth_* belongs to tests/test_verification.py, vpl_* to tests/test_vpl.py)."""
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith(("lfw_", "vpl_")))
+    """Golden vectors of the margin heads (lfw_synth_* belongs to tests/test_verification.py, vpl_* to tests/test_vpl.py, qaface_* to tests/test_qaface.py)."""
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith(("lfw_", "vpl_", "qaface_")))
 
 
 def load_golden(path):

@@ -85,14 +85,19 @@ class ShardComm:
 
 class _ShardedFusedLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, W_local, labels_local, head, margins_local, grad_enabled=True):
+    def forward(ctx, x_local, W_local, labels_local, head, margins_local, grad_enabled=True, y_g=None, engine=None):
+        # y_g / engine: Partial-FC sampling hands in the gathered labels (already remapped to the sampled class ids) and
+        # the engine sized for the sampled sub-matrix; W_local is then the gathered sub-matrix W[index]
         comm: ShardComm = head.comm
-        head.engine.prefetch_w(W_local)              # the GPU normalises the shard while the host issues the gathers
+        engine = engine or head.engine
+        engine.prefetch_w(W_local)                   # the GPU normalises the shard while the host issues the gathers
         x_g = comm.gather_rows(x_local.contiguous())
-        y_g = comm.gather_rows(labels_local.contiguous().to(torch.int64))
+        if y_g is None:
+            y_g = comm.gather_rows(labels_local.contiguous().to(torch.int64))
         margins_g = comm.gather_rows(margins_local.contiguous()) if margins_local is not None else None
-        c = head.engine.forward(x_g, W_local, y_g, head._mh_state, margins_g, update_state=True,
-                                want_grad=bool(grad_enabled and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])))
+        c = engine.forward(x_g, W_local, y_g, head._mh_state, margins_g, update_state=True,
+                           want_grad=bool(grad_enabled and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])))
+        ctx.engine = engine
         ctx.head = head
         ctx.c = c
         ctx.B_local = x_local.shape[0]
@@ -108,10 +113,10 @@ class _ShardedFusedLossFn(torch.autograd.Function):
         head = ctx.head
         if g_loss is None:
             g_loss = torch.zeros((), device=ctx.c["x_hat"].device)
-        dx, dW = head.engine.backward(ctx.c, g_loss, g_lossg, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        dx, dW = ctx.engine.backward(ctx.c, g_loss, g_lossg, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         if dx is not None and head.dx_scale != 1.0:
             dx = dx * head.dx_scale
-        return dx, dW, None, None, None, None
+        return dx, dW, None, None, None, None, None, None
 
 
 class ShardedMarginHead(nn.Module):
@@ -123,12 +128,15 @@ class ShardedMarginHead(nn.Module):
     """
 
     def __init__(self, family: str, num_classes: int, group=None, mode: str = "tc", dx_scale: float = 1.0,
-                 **ctor_kwargs):
+                 sample_rate: float = 1.0, **ctor_kwargs):
         super().__init__()
         self.family = family
         self.num_classes = num_classes
         self.comm = ShardComm(group)
         self.dx_scale = float(dx_scale)
+        if not 0.0 < sample_rate <= 1.0:
+            raise ValueError("sample_rate must be in (0, 1]")
+        self.sample_rate = float(sample_rate)
         b, e = shard_range(num_classes, self.comm.world, self.comm.rank)
         smallest = min(e_ - b_ for b_, e_ in (shard_range(num_classes, self.comm.world, r) for r in range(self.comm.world)))
         if smallest < 2:            # the same verdict on every rank (a rank raising alone would hang the others)
@@ -144,6 +152,23 @@ class ShardedMarginHead(nn.Module):
                                              c_total=num_classes)
         self.local._engine.mode = mode
         self.engine: HeadEngine = self.local._engine
+        # Partial-FC negative sampling: every step each rank keeps the classes of its shard that
+        # occur in the global batch plus random negatives, num_sample = sample_rate * ceil(C / R) per rank, and the whole
+        # fused pipeline runs on the gathered sub-matrix through a second engine of that size
+        self.num_sample = 0
+        self.sub_engine = None
+        self.last_index = None
+        if self.sample_rate < 1.0:
+            per = (num_classes + self.comm.world - 1) // self.comm.world
+            self.num_sample = max(2, int(self.sample_rate * per))
+            if self.num_sample > smallest:
+                raise ValueError(f"sample_rate {sample_rate} asks for {self.num_sample} classes per rank but the smallest shard "
+                                 f"holds {smallest}")
+            self.sub_engine = HeadEngine(self.engine.family, self.local.layout, self.num_sample, {}, mode=mode,
+                                         shard=ShardInfo(comm=self.comm, rank=self.comm.rank, world=self.comm.world,
+                                                         c_offset=self.comm.rank * self.num_sample,
+                                                         c_total=self.comm.world * self.num_sample))
+            self.sub_engine.cfg = self.engine.cfg              # same hyper-parameter block (updated in place by the head)
 
     @property
     def _mh_state(self):
@@ -163,9 +188,48 @@ class ShardedMarginHead(nn.Module):
         self.local._pre_forward(feats)
         margins = self.local._sample_margins(feats, labels)
         self.local._push_state()
-        out = _ShardedFusedLossFn.apply(feats, self.local._param(), labels, self, margins, torch.is_grad_enabled())
+        if self.sub_engine is None:
+            out = _ShardedFusedLossFn.apply(feats, self.local._param(), labels, self, margins, torch.is_grad_enabled())
+        else:
+            self.sub_engine.backward_mode = self.engine.backward_mode
+            y_g = self.comm.gather_rows(labels.contiguous().to(torch.int64))
+            index, y_sub = self.sample_classes(y_g)
+            W = self.local._param()
+            W_sub = W.index_select(0 if self.local.layout == "CD" else 1, index)      # autograd scatters dW_sub back into dW
+            out = _ShardedFusedLossFn.apply(feats, W_sub, labels, self, margins, torch.is_grad_enabled(), y_sub,
+                                            self.sub_engine)
         self.local._pull_state()
         return FusedOutput(*out)
+
+    @torch.no_grad()
+    def sample_classes(self, y_g: torch.Tensor):
+        """Partial-FC sampling on the device (no host sync): returns (index, y_sub).
+
+        index [num_sample], sorted local class ids of this rank's shard: every class of the shard that occurs in the
+        global batch y_g plus uniformly random negatives.  y_sub [B_g]: the labels in the sampled id space of the whole
+        head, rank r owning [r * num_sample, (r + 1) * num_sample) - what the engine of the sub-matrix expects.  More
+        distinct positives than num_sample in one shard poisons the loss (NaN) instead of dropping targets silently."""
+        n_local = self.c_end - self.c_begin
+        k = self.num_sample
+        dev = y_g.device
+        loc = y_g - self.c_begin
+        owned = (loc >= 0) & (loc < n_local)
+        perm = torch.rand(n_local, device=dev)
+        # positives first (insightface partial_fc.sample: perm[positive] = 2.0), as a scatter-max so that rows of other
+        # shards (clamped index, value 0) change nothing and no boolean indexing forces a host sync
+        perm.scatter_reduce_(0, loc.clamp(0, n_local - 1), torch.where(owned, 2.0, 0.0).to(perm.dtype), reduce="amax")
+        index = torch.topk(perm, k)[1].sort()[0]
+        pos = torch.searchsorted(index, loc.clamp(0, n_local - 1))
+        hit = owned & (index[pos.clamp(max=k - 1)] == loc)        # a positive that did not fit is not "hit"
+        # rows owned by this rank carry their new id, all others 0; an owned positive that was dropped carries an id outside
+        # [0, world * k) so that the prologue poisons the row (NaN loss) on every rank
+        new_id = torch.where(hit, pos + self.comm.rank * k, torch.zeros_like(pos))
+        new_id = torch.where(owned & ~hit, torch.full_like(pos, self.comm.world * k), new_id)
+        bad = (y_g < 0) | (y_g >= self.num_classes)               # never owned by anyone: poison as well
+        new_id = torch.where(bad & (self.comm.rank == 0), torch.full_like(pos, self.comm.world * k), new_id)
+        self.comm.allreduce_sum_(new_id)
+        self.last_index = index
+        return index, new_id
 
     forward = fused_loss
 

@@ -147,3 +147,30 @@ def test_mh_lib_env_selects_the_library(tmp_path, monkeypatch):
         L.load()
     monkeypatch.setenv("MH_LIB", L.LIB_PATH)
     assert L.load() is not None
+
+
+def test_partial_fc_sampling_keeps_positives_and_remaps_labels():
+    """class sampling on the device - every positive of the shard is kept, the rest are random negatives,
+    the index is sorted, labels are remapped into the sampled id space, an out-of-range label maps outside it."""
+    torch.manual_seed(0)
+    head = pkg.ShardedMarginHead("arcface", 1000, s=64.0, m=0.5, easy_margin=False, sample_rate=0.1)   # no process group: world 1
+    assert head.num_sample == 100 and head.sub_engine.C == 100
+    y = torch.randint(0, 1000, (64,))
+    index, y_sub = head.sample_classes(y)
+    assert index.shape == (100,) and bool((index[1:] > index[:-1]).all())
+    assert set(y.tolist()) <= set(index.tolist())                      # all positives sampled
+    assert torch.equal(index[y_sub], y)                                # remapped labels point at the same classes
+    index2, _ = head.sample_classes(y)
+    assert not torch.equal(index, index2)                              # the negatives are re-drawn every step
+    yb = y.clone()
+    yb[5] = 1000
+    _, y_sub_b = head.sample_classes(yb)
+    assert int(y_sub_b[5]) == 100 and torch.equal(index2[:0], index2[:0])   # id outside [0, world * k): NaN downstream
+    with pytest.raises(ValueError):
+        pkg.ShardedMarginHead("arcface", 1000, s=64.0, m=0.5, easy_margin=False, sample_rate=0.0)
+    # more distinct positives than num_sample: the dropped targets are poisoned, not silently lost
+    small = pkg.ShardedMarginHead("arcface", 1000, s=64.0, m=0.5, easy_margin=False, sample_rate=0.01)   # k = 10
+    y_many = torch.arange(0, 640, 10)                                  # 64 distinct classes
+    idx, ys = small.sample_classes(y_many)
+    kept = torch.isin(y_many, idx)
+    assert int(kept.sum()) == 10 and bool((ys[~kept] == 10).all()) and torch.equal(idx[ys[kept]], y_many[kept])

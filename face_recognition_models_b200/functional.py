@@ -285,8 +285,8 @@ class HeadEngine:
         if self.family == "vpl_arcface":
             # VPL-ArcFace (criterion.py:716-725): the GEMM runs against the mixed class vectors v_j; the per-row
             # interpolation weight a_{y_i} enters the target logit through row_params' `margins` slot
-            if exact or self.shard.world > 1:
-                raise L.MarginHeadError("VPLArcFace runs on the single-GPU tensor-core path only")
+            if exact:
+                raise L.MarginHeadError("VPLArcFace runs on the tensor-core path only")
             alpha = self._buf("vpl_alpha", (Cn,), torch.float32, dev)
             if self.vpl is not None:
                 w_gemm = self._buf("vpl_v", (C_pad, L.D), torch.bfloat16, dev)
@@ -295,7 +295,15 @@ class HeadEngine:
             else:
                 alpha.zero_()
             # the row's interpolation weight of the target column; an external target cosine is already final
-            margins = alpha[labels].contiguous() if t_ext is None else torch.zeros(B, dtype=torch.float32, device=dev)
+            if t_ext is not None:
+                margins = torch.zeros(B, dtype=torch.float32, device=dev)
+            elif self.shard.world == 1:
+                margins = alpha[labels].contiguous()
+            else:
+                # class-sharded: only the owner of y_i holds a_{y_i}; label_local is -1 elsewhere -> 0, then all-reduce(SUM)
+                ll = label_local[:B].to(torch.int64)
+                margins = torch.where(ll >= 0, alpha[ll.clamp_min(0)], torch.zeros((), dtype=torch.float32, device=dev))
+                self.shard.comm.allreduce_sum_(margins)
         elif self.family in ("elastic_cos", "elastic_arc"):
             assert margins is not None and margins.numel() == B
             margins = margins.to(device=dev, dtype=torch.float32).contiguous()

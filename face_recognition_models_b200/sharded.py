@@ -188,6 +188,8 @@ class ShardedMarginHead(nn.Module):
         self.local._pre_forward(feats)
         margins = self.local._sample_margins(feats, labels)
         self.local._push_state()
+        if self.family == "vpl_arcface":
+            self._vpl_prepare(feats, labels)
         if self.sub_engine is None:
             out = _ShardedFusedLossFn.apply(feats, self.local._param(), labels, self, margins, torch.is_grad_enabled())
         else:
@@ -200,6 +202,33 @@ class ShardedMarginHead(nn.Module):
                                             self.sub_engine)
         self.local._pull_state()
         return FusedOutput(*out)
+
+    @torch.no_grad()
+    def _vpl_prepare(self, feats: torch.Tensor, labels: torch.Tensor):
+        """VPL-ArcFace on class shards (criterion.py:703-717): the memory bank and the lifetimes are sharded like the class
+        centres; every rank refreshes the entries of ITS classes from the gathered batch, then decays its lifetimes."""
+        if self.sub_engine is not None:
+            raise L.MarginHeadError("VPLArcFace does not combine with Partial-FC sampling")
+        loc = self.local
+        if not loc.norm_training_flag:
+            self.engine.vpl = None
+            return
+        x_g = self.comm.gather_rows(feats.detach().contiguous())
+        y_g = self.comm.gather_rows(labels.contiguous().to(torch.int64)) - self.c_begin
+        n_local = self.c_end - self.c_begin
+        owned = (y_g >= 0) & (y_g < n_local)
+        x_o, y_o = x_g[owned], y_g[owned]                        # this shard's rows of the global batch (may be empty)
+        if y_o.numel() > 0:
+            uniq, inv = torch.unique(y_o, return_inverse=True)
+            sums = torch.zeros(uniq.numel(), x_o.shape[1], dtype=torch.float32, device=x_o.device)
+            sums.index_add_(0, inv, x_o.float())
+            mean = sums / torch.bincount(inv, minlength=uniq.numel()).clamp_min(1).unsqueeze(1)
+            if x_o.dtype != torch.float32:
+                mean = mean.to(x_o.dtype).float()                # the reference takes the mean in the features' dtype
+            loc.mem[uniq] = mean
+            loc.life[uniq] = float(loc.delta)
+        loc.life.sub_(1.0)
+        self.engine.vpl = dict(mem=loc.mem, life=loc.life, lamda=float(loc.lamda))
 
     @torch.no_grad()
     def sample_classes(self, y_g: torch.Tensor):

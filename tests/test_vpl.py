@@ -116,3 +116,65 @@ def test_cuda_matches_oracle_at_scale():
         assert cosim(r["dx"], ref["dx"]) >= GRAD_COS_TC and cosim(r["dW"], ref["dW"]) >= GRAD_COS_TC
         assert abs(float(r["dW"].double().norm()) - float(ref["dW"].norm())) <= 2e-3 * float(ref["dW"].norm())
         assert torch.allclose(r["mem"].double(), mem, atol=1e-5) and torch.equal(r["life"].double(), life)
+
+
+def _sharded_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import face_recognition_models_b200 as pkg
+        cfg = vo.VplConfig(easy_margin=False, lamda=0.15, delta=2)        # delta = 2: entries expire within the run
+        Bl, Cn = 48, 2001                                                   # ragged shards
+        head = pkg.ShardedMarginHead("vpl_arcface", Cn, s=cfg.s, m=cfg.m, easy_margin=cfg.easy_margin, lamda=cfg.lamda,
+                                     delta=cfg.delta).cuda()
+        b, e = head.c_begin, head.c_end
+        mem, life = torch.zeros(Cn, 512, dtype=torch.float64), torch.zeros(Cn, dtype=torch.float64)
+        for step in range(3):
+            x, W, labels = vo.make_inputs(Bl * world, Cn, 512, 70 + step)
+            with torch.no_grad():
+                head.shard_parameter().copy_(W[b:e].cuda())
+            head.shard_parameter().grad = None
+            xl = x[rank * Bl:(rank + 1) * Bl].cuda().requires_grad_(True)
+            o = head.fused_loss(xl, labels[rank * Bl:(rank + 1) * Bl].cuda())
+            o.loss.backward()
+            torch.cuda.synchronize()
+            ref = vo.loss_and_grads(cfg, x, W, labels, mem, life, True, 1.0)
+            mem, life = ref["mem"], ref["life"]
+            assert abs(float(o.loss) - float(ref["loss"])) <= LOSS_REL_TC * abs(float(ref["loss"])), (step, float(o.loss), float(ref["loss"]))
+            assert abs(float(o.acc1) - float(ref["acc1"])) < 1.1
+            assert cosim(xl.grad, ref["dx"][rank * Bl:(rank + 1) * Bl]) >= GRAD_COS_TC
+            assert cosim(head.shard_parameter().grad, ref["dW"][b:e]) >= GRAD_COS_TC
+            assert torch.allclose(head.local.mem.double().cpu(), mem[b:e], atol=1e-5)
+            assert torch.equal(head.local.life.double().cpu(), life[b:e])
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_class_sharded_vpl_matches_oracle():
+    """VPL-ArcFace with the class centres, the memory bank and the lifetimes sharded over 2 ranks (NCCL)."""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

@@ -38,6 +38,7 @@ class MhStepWs(C.Structure):
         ("rowout", C.c_void_p), ("bc", C.c_void_p), ("xs", C.c_void_p), ("rho", C.c_void_p), ("gty", C.c_void_p),
         ("dxhat_part", C.c_void_p), ("part_splits", C.c_int64), ("dxhat_full", C.c_void_p), ("gscal", C.c_void_p),
         ("r_colsum", C.c_void_p), ("rpart", C.c_void_p), ("rflag", C.c_void_p), ("dx_sync", C.c_void_p),
+        ("prog", C.c_void_p),
     ]
 
 
@@ -72,6 +73,7 @@ SIGNATURES = {
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_backward_dw_proj": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp],
+    "mh_tc_backward_dxdw": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, C.POINTER(C.c_int), _vp, _vp, _vp, _vp],
     "mh_tc_backward_dx_stash": [_cfgp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, C.POINTER(C.c_int), _vp, _vp],
     "mh_vpl_mix": [_vp, _vp, _vp, C.c_float, _i64, _i64, _vp, _vp, _vp],
     "mh_pair_cosine": [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp],
@@ -148,6 +150,8 @@ def _launches(name: str, args) -> int:
         return 0 if not getattr(args[4], "value", None) else 1
     if name == "mh_tc_backward_dx_stash":
         return 0 if not getattr(args[9], "value", None) else 1
+    if name == "mh_tc_backward_dxdw":
+        return 0 if not getattr(args[11], "value", None) else 1
     if name == "mh_step_forward":
         return 6 + (1 if int(args[8]) else 0)              # x prologue, row terms, identity fill, forward, merge, finalize (+ W prologue)
     if name == "mh_step_backward":

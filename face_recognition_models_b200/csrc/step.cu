@@ -63,6 +63,36 @@ extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int 
   MH_CHECK_ARG(n_split <= ws->part_splits, "dxhat_part holds fewer splits than mh_tc_backward_dx needs");
   const int64_t split_stride = ws->B_pad * MH_D;
   const void* xs = ws->x_hat;
+  // merged dx + dW kernel (ws->prog set, both gradients wanted, eligible shape): one launch for both backward GEMMs
+  int merged_split = 0;
+  if (ws->prog && dx && dW && ws->rpart && ws->rflag)
+    STEP_TRY(mh_tc_backward_dxdw(nullptr, ws->B_pad, ws->C, ws->C_pad, nullptr, nullptr, nullptr, nullptr, ws->layout, nullptr,
+                                 ws->ld, nullptr, &merged_split, nullptr, nullptr, nullptr, stream));
+  if (merged_split > 0) {
+    MH_CHECK_ARG(merged_split <= ws->part_splits, "dxhat_part holds fewer splits than the merged backward needs");
+    if (stash) {
+      STEP_TRY(mh_stash_prep(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
+                             ws->gty, stream));
+      xs = ws->xs;
+    } else {
+      STEP_TRY(mh_tc_backward_g(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                                ws->label_local, state, lse2, ws->bc, nullptr, stream));
+    }
+    STEP_TRY(mh_tc_backward_dxdw(ws->bc, ws->B_pad, ws->C, ws->C_pad, ws->w_hat, xs, ws->inv_norm, ws->gscal, ws->layout, dW,
+                                 ws->ld, ws->dxhat_part, &merged_split, ws->rpart, ws->rflag, ws->prog, stream));
+    if (stash) {
+      STEP_TRY(mh_stash_dx_combine(ws->dxhat_part, merged_split, split_stride, ws->rho, ws->gty, ws->label_local, ws->w_hat,
+                                   ws->B, ws->dxhat_full, stream));
+      STEP_TRY(mh_norm_backward_x(ws->dxhat_full, 1, split_stride, ws->x_hat32, ws->xnorm, ws->rowp, ws->B_pad, aux0, aux1,
+                                  ws->gscal, ws->B, dx, ws->x_dtype, stream));
+      STEP_TRY(mh_stash_dw_target(ws->gty, ws->label_local, ws->x_hat32, ws->w_hat, ws->inv_norm, ws->gscal, ws->B,
+                                  ws->layout, dW, ws->ld, stream));
+    } else {
+      STEP_TRY(mh_norm_backward_x(ws->dxhat_part, merged_split, split_stride, ws->x_hat32, ws->xnorm, ws->rowp, ws->B_pad,
+                                  aux0, aux1, ws->gscal, ws->B, dx, ws->x_dtype, stream));
+    }
+    return MH_OK;
+  }
   if (stash) {
     STEP_TRY(mh_stash_prep(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
                            ws->gty, stream));

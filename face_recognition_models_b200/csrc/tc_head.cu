@@ -34,6 +34,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int PROG_AHEAD = 48;                    // merged dx+dW kernel: max lead of one role over the other, in 256-class tiles
 constexpr int DX_SYNC_KB = 16;                    // DX lockstep: k-blocks between two rendezvous of a split's CTAs
 constexpr int STG_WARP_BYTES = 32 * 128;          // output staging per epilogue warp: 32 rows x 128 B, XOR-swizzled
 
@@ -83,6 +84,8 @@ struct TcArgs {
   float* rpart;                // DW self-projection: [4][C_pad] partial dots w^_j . dw^_j (d half x epilogue column half)
   int* rflag;                  // DW self-projection: [C_pad/128] arrival counters, zeroed before the launch
   int* dx_sync;                // DX lockstep: [n_split] arrival counters (NULL: off), zeroed before the launch
+  int dx_chunk;                // DX: k-blocks per interleaved chunk (0: contiguous splits)
+  int* prog;                   // merged dx+dW kernel: prog[0] = dx front, prog[1] = dW front (256-class tiles); NULL: off
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
   int side_mv;                 // DX side pass, MV-Softmax: invert the hard-negative re-weighting u = a*c + b as well
@@ -170,6 +173,9 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -256,6 +262,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn, int M, int
 struct Work {
   int m0, n0;        // output tile origin (rows of D, cols of D)
   int kb0, kb1;      // k-block range
+  int kb_chunk, kb_jump;   // DX interleaved split (merged dx+dW kernel): kb_chunk k-blocks every kb_jump; 0 = contiguous
   int split;         // DX split index
   int n_tile;        // FWD: class-tile index
   int m_tile;        // A-stationary modes: row-tile index (the resident x^ tile)
@@ -296,6 +303,13 @@ struct StatIter {
   }
 };
 
+// next k-block of a Work: contiguous [kb0, kb1), or chunks of kb_chunk k-blocks every kb_jump (kb_jump % kb_chunk == 0)
+__device__ __forceinline__ int kb_next(const Work& w, int kb) {
+  ++kb;
+  if (w.kb_chunk && (kb - w.kb0) % w.kb_chunk == 0) kb += w.kb_jump - w.kb_chunk;
+  return kb;
+}
+
 // The tile sequence of one CTA pair; the producer, MMA and epilogue roles all walk the same sequence.
 template <int MODE>
 struct TileLoop {
@@ -306,7 +320,7 @@ struct TileLoop {
     if (mode_astat(MODE)) si.init(a, (int)pid);
   }
   __device__ __forceinline__ bool next(const TcArgs& a, int rank, Work& w) {
-    w.split = 0; w.n_tile = 0; w.m_tile = 0;
+    w.split = 0; w.n_tile = 0; w.m_tile = 0; w.kb_chunk = 0; w.kb_jump = 0;
     if (mode_astat(MODE)) {
       int m, n;
       if (!si.next(m, n)) return false;
@@ -319,8 +333,13 @@ struct TileLoop {
       w.split = (int)(t / a.m_tiles);
       w.m0 = (int)(t % a.m_tiles) * BMT + rank * BM;
       w.n0 = 0;
-      w.kb0 = w.split * a.k_blocks_per_split;
-      w.kb1 = min(a.k_blocks_total, w.kb0 + a.k_blocks_per_split);
+      if (a.dx_chunk) {          // interleaved: split s takes chunks s, s + n_split, ... so that all pairs walk the classes together
+        w.kb_chunk = a.dx_chunk; w.kb_jump = a.dx_chunk * a.n_split;
+        w.kb0 = w.split * a.dx_chunk; w.kb1 = a.k_blocks_total;
+      } else {
+        w.kb0 = w.split * a.k_blocks_per_split;
+        w.kb1 = min(a.k_blocks_total, w.kb0 + a.k_blocks_per_split);
+      }
     } else {  // DW: 256 classes x one 256-wide half of d
       w.m0 = (int)(t >> 1) * BMT + rank * BM;
       w.n0 = (int)(t & 1) * BN;
@@ -588,10 +607,11 @@ __device__ __forceinline__ void chunk_loop(uint32_t taddr, Body&& body, Loaded&&
   }
 }
 
+// The body of one CTA of a pair: `pid` of `npid` pairs in this role (the plain kernels have one role; the merged
+// dx+dW kernel gives the first pairs the DX role and the rest the DW role).
 template <int MODE, int V>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          const __grid_constant__ TcArgs a) {
+__device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, const int64_t pid,
+                                        const int64_t npid, uint8_t* smem_raw) {
   constexpr int STAGES = mode_stages(MODE);
   constexpr int STAGE_BYTES = mode_stage_bytes(MODE);
   constexpr bool AS = mode_astat(MODE);              // x^ tile resident in smem, only w^ streams
@@ -602,10 +622,6 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr bool A_MN = (MODE == MODE_DW);
   constexpr bool B_MN = (MODE == MODE_DX || MODE == MODE_DW);
   const int rank = (int)cluster_ctarank();
-  const int64_t pid = blockIdx.x >> 1;               // tile-scheduling unit: CTA pair
-  const int64_t npid = gridDim.x >> 1;
-
-  extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;           // SWIZZLE_128B needs 1024 B alignment
   const uint32_t ares_base = smem_base;                             // AS: resident A, 8 k-blocks x 16 KB
@@ -672,8 +688,30 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           res_m = w.m_tile;
         }
         ++tile_j;
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          if (MODE == MODE_DX && a.dx_sync && ((kb - w.kb0) & (DX_SYNC_KB - 1)) == 0) {
+        if (MODE == MODE_DW && a.prog) {
+          // merged dx+dW kernel: stay within PROG_AHEAD class tiles of the dx front so that the stash and w^ tiles the dx
+          // pairs fetched are still in L2 (the role that is behind never waits: no deadlock; the leader publishes)
+          const int ct = w.m0 / BMT;
+          if (pid == 0 && rank == 0) st_relaxed_gpu(a.prog + 1, ct);
+          if (ct > ld_acquire_gpu(a.prog) + PROG_AHEAD) {
+            const long long t0 = clock64();
+            while (ct > ld_acquire_gpu(a.prog) + PROG_AHEAD) {
+              if (clock64() - t0 > 4000000000LL) __trap();
+            }
+          }
+        }
+        for (int kb = w.kb0; kb < w.kb1; kb = kb_next(w, kb)) {
+          if (MODE == MODE_DX && a.prog && w.kb_chunk && (kb - w.kb0) % w.kb_chunk == 0) {
+            const int ct = kb / w.kb_chunk;                    // 256-class tile index (dx_chunk = 4 k-blocks of 64 classes)
+            if (pid == 0 && rank == 0) st_relaxed_gpu(a.prog, ct);
+            if (ct > ld_acquire_gpu(a.prog + 1) + PROG_AHEAD) {
+              const long long t0 = clock64();
+              while (ct > ld_acquire_gpu(a.prog + 1) + PROG_AHEAD) {
+                if (clock64() - t0 > 4000000000LL) __trap();
+              }
+            }
+          }
+          if (MODE == MODE_DX && a.dx_sync && !w.kb_chunk && ((kb - w.kb0) & (DX_SYNC_KB - 1)) == 0) {
             // lockstep among the 2 * m_tiles CTAs that stream the same w^ k-blocks (one split, all row tiles): nobody
             // starts k-block group g before everybody has issued group g-1, so a w^ tile fetched from HBM for one row
             // tile is still in L2 for the others (ncu: 7.6 GB read for 6.15 GB algorithmic without it).  Single wave only
@@ -725,6 +763,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tma_load_2d_local(wtile_base + bx * (BM * 128), &a.tmW, bar_wfull, w.n0 + 64 * bx, w.m0);
         }
       }
+      // this role has issued all its loads: release the other role from the cross-role throttle
+      if ((MODE == MODE_DX || MODE == MODE_DW) && a.prog && pid == 0 && rank == 0)
+        st_relaxed_gpu(a.prog + (MODE == MODE_DW ? 1 : 0), 0x3fffffff);
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
@@ -747,7 +788,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; kb = kb_next(w, kb)) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = AS ? (ares_base + kb * A_STAGE_BYTES) : (tiles_base + stage * STAGE_BYTES);
@@ -887,7 +928,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const float thr = a.side_mv ? a.rowp[MH_RP_THR * a.ldp + w.m0 + lane + 32 * j] : 0.f;
             ucut[j] = thr + 0.5f * ((a.side_ha - 1.f) * thr + a.side_hb + lg_ha * a.side_inv_s2);
           }
-          for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          for (int kb = w.kb0; kb < w.kb1; kb = kb_next(w, kb)) {
             mbar_wait(bar_empty + 8 * side_stage, side_phase);
             const uint32_t sa = tiles_base + side_stage * STAGE_BYTES;
             uint4 q4[4];
@@ -1068,6 +1109,29 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
+}
+
+template <int MODE, int V>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  tc_body<MODE, V>(tmA, tmB, a, blockIdx.x >> 1, gridDim.x >> 1, smem_raw);   // tile-scheduling unit: CTA pair
+}
+
+// Merged backward: pairs [0, n_dx) compute dx^ partials (DX role, interleaved class chunks), the remaining pairs compute
+// dW (DW role, self-projecting).  Both roles walk the classes in the same direction and keep within PROG_AHEAD class
+// tiles of each other (TcArgs::prog), so the stash and w^ tiles are fetched from HBM once and hit in L2 for the other
+// role: 6.15 GB less DRAM traffic per step than two back-to-back kernels.  All CTAs are co-resident (grid <= #SMs, one
+// CTA per SM), which the cross-role throttle and the dW partner exchange rely on.
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_kernel_dxdw(const __grid_constant__ CUtensorMap tmA_dx, const __grid_constant__ CUtensorMap tmB_dx,
+               const __grid_constant__ TcArgs a_dx, const __grid_constant__ CUtensorMap tmA_dw,
+               const __grid_constant__ CUtensorMap tmB_dw, const __grid_constant__ TcArgs a_dw, const int n_dx) {
+  extern __shared__ uint8_t smem_raw[];
+  const int64_t pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+  if (pair < n_dx) tc_body<MODE_DX, V_NONE>(tmA_dx, tmB_dx, a_dx, pair, n_dx, smem_raw);
+  else tc_body<MODE_DW, V_NONE>(tmA_dw, tmB_dw, a_dw, pair - n_dx, pairs - n_dx, smem_raw);
 }
 
 // ---- host side: tensor maps ------------------------------------------------------------------------
@@ -1434,4 +1498,84 @@ extern "C" int mh_tc_backward_dw_proj(const void* G_bf16, int64_t B_pad, int64_t
   a.rsum = nullptr; a.rsum_parts = 0; a.rpart = rpart_ws; a.rflag = flag_ws;
   if (int e = make_tmap(&a.tmW, w_hat_bf16, C_pad, MH_D, BM)) return e;
   return launch_dw(G_bf16, B_pad, C, C_pad, x_hat_bf16, a, (cudaStream_t)stream);
+}
+
+// ---- merged backward: dx^ partials and dW in ONE persistent kernel (see tc_kernel_dxdw) ---------------------------------
+// Split of the CTA pairs between the two roles: the dx GEMM gets m_tiles * n_split pairs (~44 % of the chip: the two GEMMs
+// have the same FLOPs, the dW role also writes 4.1 GB), the dW role an even number of the rest (partner exchange).
+static int dxdw_split(int m_tiles, int pairs) {
+  if (m_tiles < 1 || m_tiles > pairs / 2) return 0;
+  int n_split = std::max(1, (int)(0.44 * pairs / m_tiles + 0.5));
+  while (n_split >= 1) {
+    const int n_dw = pairs - m_tiles * n_split;
+    if (n_dw >= 2 && n_dw % 2 == 0) return n_split;
+    --n_split;
+  }
+  return 0;
+}
+
+extern "C" int mh_tc_backward_dxdw(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* w_hat_bf16,
+                                   const void* xs_bf16, const float* inv_norm, const float* gscal, int layout, float* dW,
+                                   int64_t ld, float* dxhat_part, int* n_split_host, float* rpart_ws, int* flag_ws,
+                                   int* prog_ws, void* stream) {
+  MH_CHECK_ARG(B_pad > 0 && B_pad % BMT == 0 && C_pad > 0 && C_pad % BN == 0 && C > 0 && C <= C_pad, "bad padded shape");
+  const int pairs = num_sms() / 2;
+  const int m_tiles = (int)(B_pad / BMT);
+  const int kb_total = (int)(C_pad / BK);
+  // worth it only when every pair streams many class tiles; otherwise the caller runs the two kernels back to back
+  int n_split = (C_pad / BMT >= 8 * (int64_t)pairs) ? dxdw_split(m_tiles, pairs) : 0;
+  if (n_split > 0 && (int64_t)n_split * B_pad * MH_D * 4 > (256ll << 20)) n_split = 0;
+  if (n_split_host) *n_split_host = n_split;
+  if (!dxhat_part) return MH_OK;                                       // query
+  MH_CHECK_ARG(n_split > 0, "shape not eligible for the merged backward (query with dxhat_part == NULL first)");
+  MH_CHECK_ARG(G_bf16 && w_hat_bf16 && xs_bf16 && inv_norm && gscal && dW && rpart_ws && flag_ws && prog_ws, "null pointer");
+  MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
+  MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)dW & 15) == 0), "CD dW must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  MH_CUDA_OK(cudaMemsetAsync(flag_ws, 0, sizeof(int) * (size_t)(C_pad / BM), st));
+  MH_CUDA_OK(cudaMemsetAsync(prog_ws, 0, sizeof(int) * 2, st));
+  // DX role
+  CUtensorMap ta_dx, tb_dx, ta_dw, tb_dw;
+  if (int e = make_tmap(&ta_dx, G_bf16, (C_pad / 128) * B_pad, 128, BM)) return e;
+  if (int e = make_tmap(&tb_dx, w_hat_bf16, C_pad, MH_D, 64)) return e;
+  TcArgs ax{};
+  ax.m_tiles = m_tiles; ax.n_tiles = 1; ax.n_split = n_split;
+  ax.k_blocks_total = kb_total; ax.k_blocks_per_split = (kb_total + n_split - 1) / n_split;
+  ax.total_tiles = (int64_t)m_tiles * n_split;
+  ax.B_pad = B_pad; ax.C_pad = C_pad; ax.B = B_pad; ax.C = C_pad;
+  ax.out = dxhat_part; ax.out_split_stride = B_pad * MH_D;
+  ax.dx_chunk = BMT / BK;                                              // 4 k-blocks = one 256-class tile of the dW role
+  ax.prog = prog_ws;
+  // DW role (self-projecting)
+  if (int e = make_tmap(&ta_dw, G_bf16, (C_pad / 128) * B_pad, 128, 64)) return e;
+  if (int e = make_tmap(&tb_dw, xs_bf16, B_pad, MH_D, 64)) return e;
+  TcArgs aw{};
+  aw.out = dW; aw.raw_dw = 0; aw.layout = layout; aw.ld = ld;
+  aw.w_hat = (const __nv_bfloat16*)w_hat_bf16; aw.inv_norm = inv_norm; aw.gscal = gscal;
+  aw.rpart = rpart_ws; aw.rflag = flag_ws; aw.prog = prog_ws;
+  if (int e = make_tmap(&aw.tmW, w_hat_bf16, C_pad, MH_D, BM)) return e;
+  aw.m_tiles = (int)(C_pad / BMT); aw.n_tiles = 2; aw.n_split = 1;
+  aw.k_blocks_total = (int)(B_pad / BK); aw.k_blocks_per_split = aw.k_blocks_total;
+  aw.total_tiles = (int64_t)aw.m_tiles * 2;
+  aw.B_pad = B_pad; aw.C_pad = C_pad; aw.B = B_pad; aw.C = C;
+  static MhDeviceOnce attr_once;
+  constexpr int smem = mode_smem_bytes(MODE_DW) > mode_smem_bytes(MODE_DX) ? mode_smem_bytes(MODE_DW) : mode_smem_bytes(MODE_DX);
+  MH_CUDA_OK(mh_once_per_device(attr_once, [&] {
+    return cudaFuncSetAttribute(tc_kernel_dxdw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  }));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int n_dx = m_tiles * n_split;
+  MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel_dxdw, ta_dx, tb_dx, ax, ta_dw, tb_dw, aw, n_dx));
+  return MH_OK;
 }

@@ -66,6 +66,11 @@ def _selfproj() -> bool:
     return os.environ.get("MH_DW_SELFPROJ", "0") == "1"
 
 
+def _merged_bwd() -> bool:
+    """MH_BWD_MERGED=1 selects the merged dx + dW kernel (mh_tc_backward_dxdw) where the shape is eligible."""
+    return os.environ.get("MH_BWD_MERGED", "0") == "1"
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -361,7 +366,7 @@ class HeadEngine:
         dev = x.device
         Cn = self.C
         stash = bool(want_grad and self._stash_ok_cached())
-        key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj())
+        key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj(), _merged_bwd())
         if self._step_key != key:
             lib = L.load()
             n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
@@ -384,11 +389,19 @@ class HeadEngine:
                 T.update(bc=b("G", (B_pad, C_pad), torch.bfloat16, dev),
                          dxhat_part=b("dxhat_part", (part_splits, B_pad, L.D), torch.float32, dev),
                          gscal=b("gscal", (2,), torch.float32, dev), dx_sync=b("dx_sync", (L.DX_SYNC_INTS,), torch.int32, dev))
-                if _selfproj():
+                if _selfproj() or _merged_bwd():
                     T.update(rpart=b("dw_rpart", (4, C_pad), torch.float32, dev),
                              rflag=b("dw_rflag", (C_pad // L.TILE,), torch.int32, dev))
-                else:
+                if not _selfproj():
                     T.update(r_colsum=b("r_colsum", (B_pad // L.TILE if stash else 1, C_pad), torch.float32, dev))
+                if _merged_bwd():
+                    T.update(prog=b("bwd_prog", (2,), torch.int32, dev))
+                    ms = C.c_int(0)
+                    L.call("mh_tc_backward_dxdw", _ptr(None), B_pad, Cn, C_pad, _ptr(None), _ptr(None), _ptr(None), _ptr(None),
+                           self.layout, _ptr(None), ld, _ptr(None), C.byref(ms), _ptr(None), _ptr(None), _ptr(None), _stream())
+                    if ms.value > part_splits:
+                        part_splits = ms.value
+                        T["dxhat_part"] = b("dxhat_part", (part_splits, B_pad, L.D), torch.float32, dev)
                 if stash:
                     T.update(xs=b("xs", (B_pad, L.D), torch.bfloat16, dev), rho=b("rho", (B_pad,), torch.float32, dev),
                              gty=b("gty", (B_pad,), torch.float32, dev),

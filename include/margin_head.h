@@ -240,6 +240,20 @@ int mh_tc_backward_dw_proj(const void* G_bf16, int64_t B_pad, int64_t C, int64_t
                            const void* w_hat_bf16, const float* inv_norm, const float* gscal, int layout,
                            float* dW, int64_t ld, float* rpart_ws, int* flag_ws, void* stream);
 
+/* Merged backward (optional): the dx^ GEMM and the self-projecting dW GEMM in ONE persistent kernel.  The first
+ * m_tiles * n_split CTA pairs compute the dx^ partials over interleaved 256-class chunks, the other pairs compute dW; both
+ * roles walk the classes in the same direction and throttle each other to stay within 48 class tiles, so the B x C buffer
+ * (G or the stash) and w^ are fetched from HBM once and hit in L2 for the other role (6.15 GB less DRAM traffic per step
+ * at cfg4 than mh_tc_backward_dx + mh_tc_backward_dw_*).  No r_colsum, no dx side pass (dW projects itself).
+ * Query: dxhat_part == NULL writes the split count to *n_split_host - 0 when the shape is not eligible (fewer than 8
+ * class tiles per pair, or more row tiles than half the pairs): run the two kernels back to back then.
+ * dxhat_part [n_split, B_pad, 512]; rpart_ws [4 * C_pad] floats, flag_ws [C_pad / 128] ints, prog_ws [2] ints (scratch,
+ * zeroed here).  xs_bf16: x^ (recompute mode) or rho * x^ (stash mode), as for mh_tc_backward_dw_fused. */
+int mh_tc_backward_dxdw(const void* G_bf16, int64_t B_pad, int64_t C, int64_t C_pad, const void* w_hat_bf16,
+                        const void* xs_bf16, const float* inv_norm, const float* gscal, int layout, float* dW,
+                        int64_t ld, float* dxhat_part, int* n_split_host, float* rpart_ws, int* flag_ws,
+                        int* prog_ws, void* stream);
+
 /* ---- stash backward: O(B*d) helpers (see mh_tc_forward's stash) -------------------------------------- */
 
 /* rho_i = scale_i * 2^(ref_i - lse2_i), gty_i = G_{i,y_i} = (P_iy - 1) * dz_iy/dcos (rowout AUX0 * rowp DZT) and
@@ -355,6 +369,8 @@ typedef struct mh_step_ws {
   float* rpart;                /* [4, C_pad] or NULL */
   int32_t* rflag;              /* [C_pad / 128] or NULL */
   int32_t* dx_sync;            /* [MH_DX_SYNC_INTS] or NULL */
+  int32_t* prog;               /* [2] or NULL; non-NULL (with rpart / rflag) selects the merged dx + dW kernel
+                                  (mh_tc_backward_dxdw) whenever both gradients are wanted and the shape is eligible */
 } mh_step_ws;
 
 /* Forward of one step: mh_prologue_w (skipped when run_prologue_w == 0: w_hat / inv_norm already hold this W, e.g.

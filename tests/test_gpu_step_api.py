@@ -67,3 +67,25 @@ def test_self_projecting_dw_matches_oracle(fam, bmode, step_api, monkeypatch):
     monkeypatch.setenv("MH_DW_SELFPROJ", "0")
     base = _run(fam, bmode, B, Cn)
     assert rel(dW, base[4]) < 2e-3 and torch.equal(dx, base[3])
+
+
+@pytest.mark.parametrize("fam,bmode,B", [("arcface", "auto", 300), ("arcface", "recompute", 300), ("cosface", "auto", 1024),
+                                         ("curricularface", "auto", 700)])
+def test_merged_dx_dw_kernel_matches_oracle(fam, bmode, B, monkeypatch):
+    """MH_BWD_MERGED=1: the dx GEMM (interleaved class chunks) and the self-projecting dW GEMM as two roles of one
+    persistent kernel that throttle each other.  Same parity bar, bit-reproducible, dx bit-equal to the split kernels'
+    sum only up to the different split count (compared by tolerance)."""
+    from oracle import margin_oracle as mo
+    from tests.helpers import cosim, rel
+    Cn = 160_001                                  # 626 class tiles >= 8 per CTA pair: eligible for the merged kernel
+    monkeypatch.setenv("MH_BWD_MERGED", "1")
+    loss, a1, a5, dx, dW, (cfg, x, W, labels, margins) = _run(fam, bmode, B, Cn)
+    ref = mo.loss_and_grads(cfg, mo.HeadState(), x, W, labels, margins=margins, lambda_g=0.5)
+    assert abs(float(loss) - float(ref["loss_id"])) < 2e-3 * abs(float(ref["loss_id"]))
+    assert cosim(dx, ref["dx"]) > 0.9995 and cosim(dW, ref["dW"]) > 0.9995
+    assert rel(dW, ref["dW"]) < 1e-2 and rel(dx, ref["dx"]) < 1e-2
+    again = _run(fam, bmode, B, Cn)
+    assert torch.equal(dW, again[4]) and torch.equal(dx, again[3])
+    monkeypatch.setenv("MH_BWD_MERGED", "0")
+    base = _run(fam, bmode, B, Cn)
+    assert rel(dW, base[4]) < 2e-3 and rel(dx, base[3]) < 1e-4

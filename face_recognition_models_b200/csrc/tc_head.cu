@@ -1505,7 +1505,8 @@ extern "C" int mh_tc_backward_dw_proj(const void* G_bf16, int64_t B_pad, int64_t
 // have the same FLOPs, the dW role also writes 4.1 GB), the dW role an even number of the rest (partner exchange).
 static int dxdw_split(int m_tiles, int pairs) {
   if (m_tiles < 1 || m_tiles > pairs / 2) return 0;
-  int n_split = std::max(1, (int)(0.44 * pairs / m_tiles + 0.5));
+  static const double frac = [] { const char* e = getenv("MH_DXDW_FRAC"); return e ? atof(e) : 0.44; }();   // experiments
+  int n_split = std::max(1, (int)(frac * pairs / m_tiles + 0.5));
   while (n_split >= 1) {
     const int n_dw = pairs - m_tiles * n_split;
     if (n_dw >= 2 && n_dw % 2 == 0) return n_split;

@@ -475,6 +475,12 @@ class HeadEngine:
         split_stride = B_pad * L.D
         dxsync = self._buf("dx_sync", (L.DX_SYNC_INTS,), torch.int32, dev)
         dx = dW = None
+        if _merged_bwd() and need_dx and need_dw:
+            ms = C.c_int(0)
+            L.call("mh_tc_backward_dxdw", _ptr(None), B_pad, Cn, C_pad, _ptr(None), _ptr(None), _ptr(None), _ptr(None),
+                   self.layout, _ptr(None), ctx["ld"], _ptr(None), C.byref(ms), _ptr(None), _ptr(None), _ptr(None), st)
+            if ms.value > 0:
+                return self._backward_merged(ctx, gscal, ms.value)
         if stash is not None:
             # stash mode: G_ij = rho_i E'_ij off the target column; the target column is a sparse fp32 term.
             G = stash
@@ -518,6 +524,48 @@ class HeadEngine:
             if stash is not None:
                 L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
                        _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
+        return dx, dW
+
+    def _backward_merged(self, ctx, gscal, n_split):
+        """Both backward GEMMs in one persistent kernel (mh_tc_backward_dxdw, MH_BWD_MERGED=1): the dx role and the
+        self-projecting dW role share the stash / G and w^ through L2.  Stash or recompute mode, single GPU or sharded."""
+        dev = ctx["x_hat"].device
+        B, B_pad, C_pad, Cn = ctx["B"], ctx["B_pad"], ctx["C_pad"], self.C
+        st = _stream()
+        rowp, rowout, state = ctx["rowp"], ctx["rowout"], ctx["state"]
+        w_hat, x_hat, label_local = ctx["w_hat"], ctx["x_hat"], ctx["label_local"]
+        stash = ctx.get("stash")
+        split_stride = B_pad * L.D
+        if stash is not None:
+            G = stash
+            xs = self._buf("xs", (B_pad, L.D), torch.bfloat16, dev)
+            rho = self._buf("rho", (B_pad,), torch.float32, dev)
+            gty = self._buf("gty", (B_pad,), torch.float32, dev)
+            L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
+                   _ptr(xs), _ptr(rho), _ptr(gty), st)
+        else:
+            G = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
+            L.call("mh_tc_backward_g", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_hat), Cn, C_pad, _ptr(rowp), B_pad,
+                   _ptr(label_local), _ptr(state), _ptr(rowout[L.RO["LSE2"]]), _ptr(G), _ptr(None), st)
+            xs = x_hat
+        part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
+        rpart = self._buf("dw_rpart", (4, C_pad), torch.float32, dev)
+        rflag = self._buf("dw_rflag", (C_pad // L.TILE,), torch.int32, dev)
+        prog = self._buf("bwd_prog", (2,), torch.int32, dev)
+        dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev)
+        ns = C.c_int(0)
+        L.call("mh_tc_backward_dxdw", _ptr(G), B_pad, Cn, C_pad, _ptr(w_hat), _ptr(xs), _ptr(ctx["inv_norm"]), _ptr(gscal),
+               self.layout, _ptr(dW), ctx["ld"], _ptr(part), C.byref(ns), _ptr(rpart), _ptr(rflag), _ptr(prog), st)
+        aux0, aux1 = rowout[L.RO["AUX0"]], rowout[L.RO["AUX1"]]
+        if stash is not None:
+            full = self._buf("dxhat_full", (1, B_pad, L.D), torch.float32, dev)
+            L.call("mh_stash_dx_combine", _ptr(part), n_split, split_stride, _ptr(rho), _ptr(gty), _ptr(label_local),
+                   _ptr(w_hat), B, _ptr(full), st)
+            dx = self._finish_dx(ctx, full, 1, split_stride, gscal, aux0, aux1)
+            L.call("mh_stash_dw_target", _ptr(gty), _ptr(label_local), _ptr(ctx["x_hat32"]), _ptr(w_hat),
+                   _ptr(ctx["inv_norm"]), _ptr(gscal), B, self.layout, _ptr(dW), ctx["ld"], st)
+        else:
+            dx = self._finish_dx(ctx, part, n_split, split_stride, gscal, aux0, aux1)
         return dx, dW
 
     def _backward_vpl(self, ctx, gscal, need_dx, need_dw):

@@ -86,6 +86,7 @@ struct TcArgs {
   int* dx_sync;                // DX lockstep: [n_split] arrival counters (NULL: off), zeroed before the launch
   int dx_chunk;                // DX: k-blocks per interleaved chunk (0: contiguous splits)
   int* prog;                   // merged dx+dW kernel: prog[0] = dx front, prog[1] = dW front (256-class tiles); NULL: off
+  int prog_ahead;              // merged dx+dW kernel: max lead of one role over the other, in 256-class tiles
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
   int side_mv;                 // DX side pass, MV-Softmax: invert the hard-negative re-weighting u = a*c + b as well
@@ -206,6 +207,43 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 eviction-priority policies for the TMA loads (cache_hint operand).  The B x C stream (stash / G) is read once per
+// consumer and would otherwise push the operand that IS re-read by neighbouring pairs (w^, x^) out of L2.
+#ifndef MH_NO_L2_HINTS
+#define MH_STCS(ptr, val) __stcs((ptr), (val))
+#else
+#define MH_STCS(ptr, val) (*(ptr) = (val))
+#endif
+#ifndef MH_NO_L2_HINTS
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+#else
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
+#endif
+// as tma_load_2d_2sm, with an L2 cache policy (0 = none)
+__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                     uint64_t policy) {
+#ifndef MH_NO_L2_HINTS
+  if (policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+    return;
+  }
+#endif
+  tma_load_2d_2sm(dst, map, bar, c0, c1);
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -584,7 +622,8 @@ __device__ __forceinline__ void flush_tile(const uint8_t* stg, int lane, uint8_t
   for (int i2 = 0; i2 < 8; ++i2) {
     const int rr = 4 * i2 + (lane >> 3);
     const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) * 16));
-    if (rr < rows_ok) *reinterpret_cast<uint4*>(dst + (int64_t)rr * pitch_bytes + (lane & 7) * 16) = val;
+    // written once, not re-read by this kernel: streaming store (evict-first in L2), keeps the operands resident
+    if (rr < rows_ok) MH_STCS(reinterpret_cast<uint4*>(dst + (int64_t)rr * pitch_bytes + (lane & 7) * 16), val);
   }
 }
 
@@ -678,6 +717,11 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
       Work w;
       int res_m = -1;
       uint32_t tile_j = 0;
+      // L2 priorities.  DX: the stash / G tile is read by exactly one pair (evict first; in the merged kernel the dW
+      // role still wants it: normal), w^ by every row tile of the split (evict last).  DW: x^ is the 1 MB every tile
+      // re-reads (evict last).
+      const uint64_t pol_a = (MODE == MODE_DX && !a.prog) ? l2_policy_evict_first() : 0;
+      const uint64_t pol_b = (MODE == MODE_DX || MODE == MODE_DW) ? l2_policy_evict_last() : 0;
       while (tl.next(a, rank, w)) {
         if (AS && w.m_tile != res_m) {
           // (re)load the resident x^ tile: wait until every MMA of the previous tiles has retired
@@ -693,9 +737,9 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
           // pairs fetched are still in L2 (the role that is behind never waits: no deadlock; the leader publishes)
           const int ct = w.m0 / BMT;
           if (pid == 0 && rank == 0) st_relaxed_gpu(a.prog + 1, ct);
-          if (ct > ld_acquire_gpu(a.prog) + PROG_AHEAD) {
+          if (ct > ld_acquire_gpu(a.prog) + a.prog_ahead) {
             const long long t0 = clock64();
-            while (ct > ld_acquire_gpu(a.prog) + PROG_AHEAD) {
+            while (ct > ld_acquire_gpu(a.prog) + a.prog_ahead) {
               if (clock64() - t0 > 4000000000LL) __trap();
             }
           }
@@ -704,9 +748,9 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
           if (MODE == MODE_DX && a.prog && w.kb_chunk && (kb - w.kb0) % w.kb_chunk == 0) {
             const int ct = kb / w.kb_chunk;                    // 256-class tile index (dx_chunk = 4 k-blocks of 64 classes)
             if (pid == 0 && rank == 0) st_relaxed_gpu(a.prog, ct);
-            if (ct > ld_acquire_gpu(a.prog + 1) + PROG_AHEAD) {
+            if (ct > ld_acquire_gpu(a.prog + 1) + a.prog_ahead) {
               const long long t0 = clock64();
-              while (ct > ld_acquire_gpu(a.prog + 1) + PROG_AHEAD) {
+              while (ct > ld_acquire_gpu(a.prog + 1) + a.prog_ahead) {
                 if (clock64() - t0 > 4000000000LL) __trap();
               }
             }
@@ -735,7 +779,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
           if (rank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES); else mbar_arrive_cluster(fb, 0);
           if (MODE == MODE_DX) {
             // A = G, class-tiled [C_pad/128][B_pad][128]: k-block kb = classes 64kb.. -> slab kb/2, columns (kb&1)*64
-            tma_load_2d_2sm(sa, &tmA, fb, (kb & 1) * 64, (kb >> 1) * (int)a.B_pad + w.m0);   // box [64 k][128 rows]
+            tma_load_2d_2sm_hint(sa, &tmA, fb, (kb & 1) * 64, (kb >> 1) * (int)a.B_pad + w.m0, pol_a);   // box [64 k][128 rows]
           } else if (MODE == MODE_DW) {
             // A = G^T from the class-tiled G: this CTA's 128 classes are slab m0/128; boxes [64 classes][64 rows]
 #pragma unroll
@@ -749,7 +793,8 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
             for (int nh = 0; nh < BNT / BN; ++nh)
 #pragma unroll
               for (int bx = 0; bx < GW / 64; ++bx)
-                tma_load_2d_2sm(sb + (nh * (GW / 64) + bx) * 8192, &tmB, fb, w.n0 + nh * BN + rank * GW + 64 * bx, kb * BK);
+                tma_load_2d_2sm_hint(sb + (nh * (GW / 64) + bx) * 8192, &tmB, fb, w.n0 + nh * BN + rank * GW + 64 * bx, kb * BK,
+                                     pol_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -987,7 +1032,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
           float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + cbase + c * 32;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            reinterpret_cast<uint4*>(dst)[k] = make_uint4(cur[4 * k], cur[4 * k + 1], cur[4 * k + 2], cur[4 * k + 3]);
+            MH_STCS(reinterpret_cast<uint4*>(dst) + k, make_uint4(cur[4 * k], cur[4 * k + 1], cur[4 * k + 2], cur[4 * k + 3]));
         }, release);
       } else {
         // ---- DW: this thread owns class `row` and 128 of the tile's 256 d columns ----
@@ -1095,7 +1140,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
           } else if (ok) {
             // parameter layout [D, C]: for a fixed d the 32 lanes are 32 consecutive classes -> coalesced directly
 #pragma unroll
-            for (int k = 0; k < 32; ++k) a.out[(int64_t)(w.n0 + cbase + c * 32 + k) * a.ld + row] = o[k];
+            for (int k = 0; k < 32; ++k) MH_STCS(a.out + (int64_t)(w.n0 + cbase + c * 32 + k) * a.ld + row, o[k]);
           }
         }, release);
       }
@@ -1547,13 +1592,15 @@ extern "C" int mh_tc_backward_dxdw(const void* G_bf16, int64_t B_pad, int64_t C,
   ax.out = dxhat_part; ax.out_split_stride = B_pad * MH_D;
   ax.dx_chunk = BMT / BK;                                              // 4 k-blocks = one 256-class tile of the dW role
   ax.prog = prog_ws;
+  static const int env_ahead = [] { const char* e = getenv("MH_PROG_AHEAD"); return e ? atoi(e) : 0; }();   // experiments
+  ax.prog_ahead = env_ahead > 0 ? env_ahead : PROG_AHEAD;
   // DW role (self-projecting)
   if (int e = make_tmap(&ta_dw, G_bf16, (C_pad / 128) * B_pad, 128, 64)) return e;
   if (int e = make_tmap(&tb_dw, xs_bf16, B_pad, MH_D, 64)) return e;
   TcArgs aw{};
   aw.out = dW; aw.raw_dw = 0; aw.layout = layout; aw.ld = ld;
   aw.w_hat = (const __nv_bfloat16*)w_hat_bf16; aw.inv_norm = inv_norm; aw.gscal = gscal;
-  aw.rpart = rpart_ws; aw.rflag = flag_ws; aw.prog = prog_ws;
+  aw.rpart = rpart_ws; aw.rflag = flag_ws; aw.prog = prog_ws; aw.prog_ahead = ax.prog_ahead;
   if (int e = make_tmap(&aw.tmW, w_hat_bf16, C_pad, MH_D, BM)) return e;
   aw.m_tiles = (int)(C_pad / BMT); aw.n_tiles = 2; aw.n_split = 1;
   aw.k_blocks_total = (int)(B_pad / BK); aw.k_blocks_per_split = aw.k_blocks_total;

@@ -39,9 +39,9 @@ def measure(tag):
 
 # settings: "ENV=VAL,ENV=VAL;..." (MH_BACKWARD sets head.backward_mode); each measured twice, interleaved
 settings = [dict(kv.split("=") for kv in grp.split(",") if kv) for grp in os.environ.get("SETTINGS", "").split(";")]
-for rep in range(2):
+for rep in range(int(os.environ.get("REPS", 2))):
     for st in settings:
-        for k in [k for k in os.environ if k.startswith("MH_") and k not in ("MH_LIB",)]:
+        for k in [k for k in os.environ if k.startswith("MH_") and k not in ("MH_LIB", "MH_DXDW_FRAC", "MH_PROG_AHEAD")]:
             os.environ.pop(k, None)      # experiment toggles are per setting
         head.backward_mode = "auto"
         for k, v in st.items():

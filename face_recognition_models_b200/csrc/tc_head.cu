@@ -34,7 +34,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int PROG_AHEAD = 48;                    // merged dx+dW kernel: max lead of one role over the other, in 256-class tiles
+constexpr int PROG_AHEAD = 16;                    // merged dx+dW kernel: max lead of one role over the other, in 256-class tiles
 constexpr int DX_SYNC_KB = 16;                    // DX lockstep: k-blocks between two rendezvous of a split's CTAs
 constexpr int STG_WARP_BYTES = 32 * 128;          // output staging per epilogue warp: 32 rows x 128 B, XOR-swizzled
 
@@ -208,14 +208,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
-// L2 eviction-priority policies for the TMA loads (cache_hint operand).  The B x C stream (stash / G) is read once per
-// consumer and would otherwise push the operand that IS re-read by neighbouring pairs (w^, x^) out of L2.
-#ifndef MH_NO_L2_HINTS
+// L2 eviction-priority policies for the TMA loads (cache_hint operand) and streaming stores - EXPERIMENT, compiled in
+// with -DMH_L2_HINTS only.  Idea: the B x C stream (stash / G) is read once per consumer and pushes the operand that IS
+// re-read by neighbouring pairs (w^, x^) out of L2.  Measured (profiles/r2_ab_merged_hints.txt, ncu): evict-first on the
+// stash + evict-last on w^ RAISED the dx kernel's DRAM reads from 7.65 to 9.17 GB and made the merged backward slower
+// than the two separate kernels; without hints the merged kernel is 0.4 ms faster.  Off by default.
+#ifdef MH_L2_HINTS
 #define MH_STCS(ptr, val) __stcs((ptr), (val))
 #else
 #define MH_STCS(ptr, val) (*(ptr) = (val))
 #endif
-#ifndef MH_NO_L2_HINTS
+#ifdef MH_L2_HINTS
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -233,7 +236,7 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0; }
 // as tma_load_2d_2sm, with an L2 cache policy (0 = none)
 __device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                                      uint64_t policy) {
-#ifndef MH_NO_L2_HINTS
+#ifdef MH_L2_HINTS
   if (policy) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
@@ -1546,11 +1549,12 @@ extern "C" int mh_tc_backward_dw_proj(const void* G_bf16, int64_t B_pad, int64_t
 }
 
 // ---- merged backward: dx^ partials and dW in ONE persistent kernel (see tc_kernel_dxdw) ---------------------------------
-// Split of the CTA pairs between the two roles: the dx GEMM gets m_tiles * n_split pairs (~44 % of the chip: the two GEMMs
-// have the same FLOPs, the dW role also writes 4.1 GB), the dW role an even number of the rest (partner exchange).
+// Split of the CTA pairs between the two roles: the dx GEMM gets m_tiles * n_split pairs (~38 % of the chip: the two GEMMs
+// have the same FLOPs, the dW role also writes 4.1 GB of fp32 dW and projects), the dW role an even number of the rest
+// (partner exchange).
 static int dxdw_split(int m_tiles, int pairs) {
   if (m_tiles < 1 || m_tiles > pairs / 2) return 0;
-  static const double frac = [] { const char* e = getenv("MH_DXDW_FRAC"); return e ? atof(e) : 0.44; }();   // experiments
+  static const double frac = [] { const char* e = getenv("MH_DXDW_FRAC"); return e ? atof(e) : 0.38; }();   // measured best of 0.38 / 0.44 / 0.49
   int n_split = std::max(1, (int)(frac * pairs / m_tiles + 0.5));
   while (n_split >= 1) {
     const int n_dw = pairs - m_tiles * n_split;

@@ -16,6 +16,8 @@ TC_MODES = ["mh_tc_forward", "mh_tc_forward", "mh_tc_backward_g", "mh_tc_backwar
 
 def api_name(kernel):
     import re
+    if "tc_kernel_dxdw" in kernel:
+        return "mh_tc_backward_dxdw"
     m = re.search(r"tc_kernel<\(?(?:int\))?(\d)", kernel)
     if m:
         return TC_MODES[int(m.group(1))]

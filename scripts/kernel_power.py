@@ -65,8 +65,10 @@ keep = []
 
 
 def record(mode, grad=True):
+    """One step through the per-kernel driver (MH_STEP_API=0) so that every entry point is seen by the hook."""
     global rec
     head.backward_mode = mode
+    os.environ["MH_STEP_API"] = "0"
     for _ in range(2):
         xg = x.detach().requires_grad_(grad)
         head._param().grad = None
@@ -83,6 +85,7 @@ def record(mode, grad=True):
         out.loss.backward()
     keep.append((xg, out, head._param().grad))
     torch.cuda.synchronize()
+    os.environ.pop("MH_STEP_API", None)
     r, rec = rec, None
     return r
 
@@ -125,7 +128,7 @@ def replay(tag, name, args):
 
 
 BIG = ("mh_prologue_w", "mh_tc_forward", "mh_tc_backward_g", "mh_tc_backward_dx", "mh_tc_backward_dx_stash",
-       "mh_tc_backward_dw_fused", "mh_tc_backward_dw", "mh_tc_backward_dw_proj")
+       "mh_tc_backward_dw_fused", "mh_tc_backward_dw", "mh_tc_backward_dw_proj", "mh_tc_backward_dxdw")
 for tag, mode, grad in (("stash", "auto", True), ("recompute", "recompute", True), ("nograd", "auto", False)):
     if ONLY and tag not in ONLY:
         continue
@@ -134,7 +137,10 @@ for tag, mode, grad in (("stash", "auto", True), ("recompute", "recompute", True
     for name, args in calls:
         if name not in BIG or name in seen:
             continue
-        if name.startswith("mh_tc_backward_dx") and not getattr(args[4 if name == "mh_tc_backward_dx" else 9], "value", None):
+        if name == "mh_tc_backward_dxdw":
+            if not getattr(args[11], "value", None):
+                continue                              # the eligibility query, no launch
+        elif name.startswith("mh_tc_backward_dx") and not getattr(args[4 if name == "mh_tc_backward_dx" else 9], "value", None):
             continue                                  # the split-count query, no launch
         if tag != "stash" and name == "mh_prologue_w":
             continue

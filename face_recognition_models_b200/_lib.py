@@ -38,7 +38,7 @@ class MhStepWs(C.Structure):
         ("rowout", C.c_void_p), ("bc", C.c_void_p), ("xs", C.c_void_p), ("rho", C.c_void_p), ("gty", C.c_void_p),
         ("dxhat_part", C.c_void_p), ("part_splits", C.c_int64), ("dxhat_full", C.c_void_p), ("gscal", C.c_void_p),
         ("r_colsum", C.c_void_p), ("rpart", C.c_void_p), ("rflag", C.c_void_p), ("dx_sync", C.c_void_p),
-        ("prog", C.c_void_p),
+        ("pw_ready", C.c_void_p), ("prog", C.c_void_p),
     ]
 
 
@@ -70,6 +70,8 @@ SIGNATURES = {
     "mh_prologue_x": [_vp, _i32, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "mh_row_params": [_cfgp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_forward": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "mh_tc_forward_pw": [_cfgp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
+                         C.POINTER(C.c_int), _vp],
     "mh_tc_backward_g": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_backward_dw_fused": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i64, _vp],
     "mh_tc_backward_dw_proj": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp],

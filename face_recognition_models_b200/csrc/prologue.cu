@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
   const float inv = 1.f / fmaxf(nrm, 1e-12f);
   const int64_t y = labels[row] - c_offset;
   const bool owned = (y >= 0 && y < C);
-  float dot = 0.f;
+  float dot = 0.f, wss = 0.f;       // wss: |w_y|^2 of the gathered row, same summation order as prologue_w_cd_kernel
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float4 o = make_float4(v[k * 4 + 0] * inv, v[k * 4 + 1] * inv, v[k * 4 + 2] * inv, v[k * 4 + 3] * inv);
@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
       if (layout == MH_LAYOUT_CD) {
         float4 w = __ldg(reinterpret_cast<const float4*>(W + y * ld + d));
         dot += o.x * w.x + o.y * w.y + o.z * w.z + o.w * w.w;
+        wss += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
       } else {
         dot += o.x * __ldg(W + (int64_t)(d + 0) * ld + y) + o.y * __ldg(W + (int64_t)(d + 1) * ld + y) +
                o.z * __ldg(W + (int64_t)(d + 2) * ld + y) + o.w * __ldg(W + (int64_t)(d + 3) * ld + y);
@@ -581,13 +582,19 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
     }
   }
   dot = warp_sum(dot);
+  // inv_norm == NULL (merged prologue + forward: 1/|w| is not written yet): take the norm of the gathered row here
+  float inv_w = 0.f;
+  if (inv_norm == nullptr) {
+    wss = warp_sum(wss);
+    inv_w = 1.f / fmaxf(sqrtf(wss), 1e-12f);
+  }
   if (lane == 0) {
     xnorm[row] = nrm;
     // a label outside [0, c_total) (the whole head, all shards) poisons the row's target cosine, so the loss comes out
     // NaN instead of silently dropping the target (the reference's one_hot.scatter_ raises a device assert there);
     // sharded: a valid label owned by another rank contributes 0 to the all-reduce(SUM) of t_raw, NaN survives it
     const bool valid = labels[row] >= 0 && labels[row] < c_total;
-    t_raw[row] = owned ? dot * inv_norm[y] : (valid ? 0.f : __int_as_float(0x7fc00000));
+    t_raw[row] = owned ? dot * (inv_norm ? inv_norm[y] : inv_w) : (valid ? 0.f : __int_as_float(0x7fc00000));
     label_local[row] = owned ? (int32_t)y : -1;
   }
 }
@@ -596,7 +603,8 @@ extern "C" int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pa
                              const float* W, int layout, int64_t C, int64_t ld, int64_t c_offset,
                              const float* inv_norm, void* x_hat_bf16, float* x_hat32, float* xnorm, float* t_raw,
                              int32_t* label_local, int64_t c_total, void* stream) {
-  MH_CHECK_ARG(x && labels && W && inv_norm && x_hat_bf16 && x_hat32 && xnorm && t_raw && label_local, "null pointer");
+  MH_CHECK_ARG(x && labels && W && x_hat_bf16 && x_hat32 && xnorm && t_raw && label_local, "null pointer");
+  MH_CHECK_ARG(inv_norm || layout == MH_LAYOUT_CD, "inv_norm may be NULL (norm taken from the gathered row) for the [C, 512] layout only");
   MH_CHECK_ARG(B > 0 && B_pad >= B && B_pad % MH_TILE == 0, "B_pad must be a multiple of 128 and >= B");
   MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
   MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)W & 15) == 0), "CD weight must be 16-byte aligned");

@@ -28,14 +28,25 @@ extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const
   STEP_TRY(check_ws(ws));
   MH_CHECK_ARG(!stash || ws->bc, "stash requested without a B x C buffer");
   MH_CHECK_ARG(ws->n_tiles == mh_fwd_num_tiles(ws->C_pad), "stats_tiles must hold mh_fwd_num_tiles records");
-  if (run_prologue_w)
+  // merged prologue + forward (ws->pw_ready set, the W prologue has to run, eligible head / shape): the prologue becomes
+  // a role of the forward launch; 1/|w_y| of the target rows is then taken by the x prologue from the gathered rows
+  int pw_ok = 0;
+  if (run_prologue_w && ws->pw_ready)
+    STEP_TRY(mh_tc_forward_pw(cfg, nullptr, ws->B, ws->B_pad, W, ws->layout, ws->ld, nullptr, nullptr, ws->C, ws->C_pad, nullptr,
+                              ws->B_pad, nullptr, nullptr, nullptr, stash ? ws->bc : nullptr, nullptr, &pw_ok, stream));
+  if (run_prologue_w && !pw_ok)
     STEP_TRY(mh_prologue_w(W, ws->layout, ws->C, ws->ld, ws->w_hat, ws->C_pad, nullptr, ws->inv_norm, stream));
   STEP_TRY(mh_prologue_x(x, ws->x_dtype, ws->B, ws->B_pad, labels, W, ws->layout, ws->C, ws->ld, /*c_offset=*/0,
-                         ws->inv_norm, ws->x_hat, ws->x_hat32, ws->xnorm, ws->t_raw, ws->label_local, /*c_total=*/ws->C,
-                         stream));
+                         pw_ok ? nullptr : ws->inv_norm, ws->x_hat, ws->x_hat32, ws->xnorm, ws->t_raw, ws->label_local,
+                         /*c_total=*/ws->C, stream));
   STEP_TRY(mh_row_params(cfg, ws->B, ws->xnorm, ws->t_raw, margins, state, update_state, ws->rowp, ws->B_pad, stream));
-  STEP_TRY(mh_tc_forward(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
-                         ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr, stream));
+  if (pw_ok)
+    STEP_TRY(mh_tc_forward_pw(cfg, ws->x_hat, ws->B, ws->B_pad, W, ws->layout, ws->ld, ws->w_hat, ws->inv_norm, ws->C, ws->C_pad,
+                              ws->rowp, ws->B_pad, ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr,
+                              ws->pw_ready, &pw_ok, stream));
+  else
+    STEP_TRY(mh_tc_forward(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                           ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr, stream));
   STEP_TRY(mh_merge_stats(ws->stats_tiles, ws->n_tiles, ws->B, ws->B_pad, ws->merge_scratch, ws->stats, stream));
   STEP_TRY(mh_finalize_rows(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, cfg->family == MH_SPHEREFACE ? 1 : 0,
                             ws->rowout, ws->B_pad, scalars, state, stream));

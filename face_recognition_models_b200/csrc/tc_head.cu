@@ -87,6 +87,8 @@ struct TcArgs {
   int dx_chunk;                // DX: k-blocks per interleaved chunk (0: contiguous splits)
   int* prog;                   // merged dx+dW kernel: prog[0] = dx front, prog[1] = dW front (256-class tiles); NULL: off
   int prog_ahead;              // merged dx+dW kernel: max lead of one role over the other, in 256-class tiles
+  const int* w_ready;          // merged prologue+forward kernel: per 256-class tile, #rows of w^ written so far (NULL: off)
+  int* fwd_front;              // merged prologue+forward kernel: class tile the forward leader pair is loading
   const float* rho;            // DX side pass: rho_i of the stash rows (NULL: no side pass)
   float side_kappa, side_inv_s2;   // DX side pass: cos = log2(E') * inv_s2 + kappa
   int side_mv;                 // DX side pass, MV-Softmax: invert the hard-negative re-weighting u = a*c + b as well
@@ -735,6 +737,20 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
           res_m = w.m_tile;
         }
         ++tile_j;
+        if (AS && a.w_ready) {
+          // merged prologue+forward kernel: this class tile of w^ is being written by the prologue role of the same
+          // launch; wait for all 256 rows (release / acquire on the tile's counter), then order the generic-proxy writes
+          // before this thread's TMA (async-proxy) reads
+          if (pid == 0 && rank == 0) st_relaxed_gpu(a.fwd_front, w.n_tile);
+          const int* rdy = a.w_ready + w.n_tile;
+          if (ld_acquire_gpu(rdy) < BN) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(rdy) < BN) {
+              if (clock64() - t0 > 4000000000LL) __trap();
+            }
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         if (MODE == MODE_DW && a.prog) {
           // merged dx+dW kernel: stay within PROG_AHEAD class tiles of the dx front so that the stash and w^ tiles the dx
           // pairs fetched are still in L2 (the role that is behind never waits: no deadlock; the leader publishes)
@@ -814,6 +830,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
       // this role has issued all its loads: release the other role from the cross-role throttle
       if ((MODE == MODE_DX || MODE == MODE_DW) && a.prog && pid == 0 && rank == 0)
         st_relaxed_gpu(a.prog + (MODE == MODE_DW ? 1 : 0), 0x3fffffff);
+      if (AS && a.w_ready && pid == 0 && rank == 0) st_relaxed_gpu(a.fwd_front, 0x3fffffff);
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
@@ -1180,6 +1197,89 @@ tc_kernel_dxdw(const __grid_constant__ CUtensorMap tmA_dx, const __grid_constant
   const int64_t pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
   if (pair < n_dx) tc_body<MODE_DX, V_NONE>(tmA_dx, tmB_dx, a_dx, pair, n_dx, smem_raw);
   else tc_body<MODE_DW, V_NONE>(tmA_dw, tmB_dw, a_dw, pair - n_dx, pairs - n_dx, smem_raw);
+}
+
+// ---- merged W prologue + forward -------------------------------------------------------------------------
+// The W prologue ([C, 512] layout) as a ROLE of the forward launch: a few CTA pairs normalise the class centres tile by
+// tile (fp32 W -> bf16 w^ + 1/|w|), the other pairs run the fused forward and pick every w^ tile up from L2 right after
+// it was written.  The HBM-bound prologue (0.87 ms alone at cfg4) disappears under the tensor-bound forward and the
+// forward's 2.05 GB read of w^ never reaches DRAM.  Protocol: per 256-class tile a counter of finished rows
+// (red.release after the rows' stores; the forward producer acquires it, then fence.proxy.async before its TMA loads);
+// the prologue role stays at most PW_AHEAD tiles ahead of the forward front (L2 residency), and only the role that is
+// ahead ever waits.  Bounded spins, all CTAs resident (grid = #SMs).
+constexpr int PW_AHEAD = 64;
+struct PwArgs {
+  const float* W;
+  int64_t C, C_pad, ld;
+  __nv_bfloat16* what;
+  float* inv_norm;
+  int* ready;                  // [C_pad / 256]
+  const int* fwd_front;
+};
+
+// one warp normalises 4 consecutive classes per step (16 float4 loads in flight per lane); same arithmetic, same
+// summation order as prologue_w_cd_kernel (prologue.cu), so w^ and inv_norm are bit-identical to the stand-alone prologue
+__device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int WARPS = NUM_THREADS / 32;
+  const int64_t groups = p.C_pad / 4;
+  for (int64_t g = (int64_t)cta * WARPS + warp; g < groups; g += (int64_t)ncta * WARPS) {
+    const int64_t row0 = g * 4;
+    const int tile = (int)(row0 / BN);
+    if (tile > ld_acquire_gpu(p.fwd_front) + PW_AHEAD) {
+      const long long t0 = clock64();
+      while (tile > ld_acquire_gpu(p.fwd_front) + PW_AHEAD) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    float4 v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t row = row0 + r;
+      const float4* src = reinterpret_cast<const float4*>(p.W + row * p.ld);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[r][k] = (row < p.C) ? __ldg(src + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t row = row0 + r;
+      uint2* dst = reinterpret_cast<uint2*>(p.what + row * MH_D);
+      if (row >= p.C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = make_uint2(0u, 0u);
+        continue;
+      }
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ss += v[r][k].x * v[r][k].x + v[r][k].y * v[r][k].y + v[r][k].z * v[r][k].z + v[r][k].w * v[r][k].w;
+      ss = warp_sum(ss);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      if (lane == 0) p.inv_norm[row] = inv;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 o = make_float4(v[r][k].x * inv, v[r][k].y * inv, v[r][k].z * inv, v[r][k].w * inv);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        dst[lane + 32 * k] = pk;
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) red_release_gpu_add(p.ready + tile, 4);
+  }
+}
+
+template <int MODE, int V>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_kernel_pwfwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ TcArgs a, const PwArgs pw, const int n_pw) {
+  extern __shared__ uint8_t smem_raw[];
+  const int64_t pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+  if (pair < n_pw) pw_role(pw, (int)blockIdx.x, 2 * n_pw);
+  else tc_body<MODE, V>(tmA, tmB, a, pair - n_pw, pairs - n_pw, smem_raw);
 }
 
 // ---- host side: tensor maps ------------------------------------------------------------------------
@@ -1630,4 +1730,96 @@ extern "C" int mh_tc_backward_dxdw(const void* G_bf16, int64_t B_pad, int64_t C,
   const int n_dx = m_tiles * n_split;
   MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel_dxdw, ta_dx, tb_dx, ax, ta_dw, tb_dw, aw, n_dx));
   return MH_OK;
+}
+
+// ---- merged W prologue + forward: host side ------------------------------------------------------------------------
+template <int MODE, int V>
+static int launch_pwfwd(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, const PwArgs& pw, int n_pw,
+                        int pairs, cudaStream_t st) {
+  static MhDeviceOnce attr_once;
+  constexpr int smem = mode_smem_bytes(MODE);
+  MH_CUDA_OK(mh_once_per_device(attr_once, [&] {
+    return cudaFuncSetAttribute(tc_kernel_pwfwd<MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  }));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel_pwfwd<MODE, V>, ta, tb, args, pw, n_pw));
+  return MH_OK;
+}
+
+// pairs given to the prologue role: the forward keeps a multiple of m_tiles pairs (no left-over pairs, whose tail tiles
+// would have to wait for the whole prologue), the prologue role gets the rest (>= MH_PW_PAIRS, default 12)
+static int pwfwd_split(int m_tiles, int pairs) {
+  static const int want = [] { const char* e = getenv("MH_PW_PAIRS"); return e ? atoi(e) : 12; }();
+  if (m_tiles < 1 || want < 2) return 0;
+  const int n_fwd = ((pairs - want) / m_tiles) * m_tiles;
+  const int n_pw = pairs - n_fwd;
+  return (n_fwd >= m_tiles && n_pw <= pairs / 3) ? n_pw : 0;
+}
+
+extern "C" int mh_tc_forward_pw(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const float* W,
+                                int layout, int64_t ld, void* w_hat_bf16, float* inv_norm, int64_t C, int64_t C_pad,
+                                const float* rowp, int64_t ldp, const int32_t* label_local, const float* state,
+                                float* stats_tiles, void* stash_bf16, int* ready_ws, int* eligible_host, void* stream) {
+  MH_CHECK_ARG(cfg_host, "null pointer");
+  if (int e = check_common(B, B_pad, C, C_pad)) return e;
+  const int pairs = num_sms() / 2;
+  const int m_tiles = (int)(B_pad / BMT);
+  const MhParams p = mh_make_params(cfg_host);
+  const int v = variant_of(p);
+  int n_pw = 0;
+  // [C, 512] parameters only (ArcFace, SphereFace, MV-Softmax), one launch of row tiles, many class tiles per pair
+  if (layout == MH_LAYOUT_CD && ld % 4 == 0 && p.family != MH_VPL_ARC && (v == V_PLAIN || v == V_MV || (v == V_SPHERE && !stash_bf16)) &&
+      C_pad / BN >= 8 * (int64_t)pairs)
+    n_pw = pwfwd_split(m_tiles, pairs);
+  if (eligible_host) *eligible_host = n_pw > 0 ? 1 : 0;
+  if (!x_hat_bf16) return MH_OK;                                           // query
+  MH_CHECK_ARG(n_pw > 0, "shape / head not eligible for the merged prologue + forward (query with x_hat == NULL first)");
+  MH_CHECK_ARG(W && w_hat_bf16 && inv_norm && rowp && label_local && state && stats_tiles && ready_ws, "null pointer");
+  MH_CHECK_ARG(((uintptr_t)W & 15) == 0 && ldp >= B_pad, "W must be 16-byte aligned; rowp pitch must cover B_pad");
+  if (stash_bf16) MH_CHECK_ARG(mh_tc_stash_ok(cfg_host, C), "head not eligible for the forward stash (see mh_tc_stash_ok)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_fwd = pairs - n_pw;
+  const int n_ct = (int)(C_pad / BN);
+  MH_CUDA_OK(cudaMemsetAsync(ready_ws, 0, sizeof(int) * (size_t)(n_ct + 1), st));
+  {
+    const int64_t n = 2 * (int64_t)pairs * MH_ST_PLANES * B_pad;
+    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * pairs, B_pad);
+  }
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN / 2)) return e;
+  if (int e = make_tmap(&ta, x_hat_bf16, B_pad, MH_D, BM)) return e;
+  TcArgs a{};
+  a.m_tiles = m_tiles; a.n_tiles = n_ct; a.n_split = 1;
+  a.k_blocks_total = MH_D / BK; a.k_blocks_per_split = a.k_blocks_total;
+  a.total_tiles = (int64_t)a.m_tiles * a.n_tiles;
+  make_sched(a, n_fwd);
+  a.p = p;
+  a.fixref = mh_tc_fixref_ok(cfg_host, C);
+  a.umax = family_umax(a.p);
+  a.B = B; a.C = C; a.B_pad = B_pad; a.C_pad = C_pad;
+  a.rowp = rowp; a.ldp = ldp; a.label_local = label_local; a.state = state;
+  a.stats_tiles = stats_tiles;
+  a.G = (__nv_bfloat16*)stash_bf16;
+  a.w_ready = ready_ws; a.fwd_front = ready_ws + n_ct;
+  PwArgs pw{};
+  pw.W = W; pw.C = C; pw.C_pad = C_pad; pw.ld = ld;
+  pw.what = (__nv_bfloat16*)w_hat_bf16; pw.inv_norm = inv_norm; pw.ready = ready_ws; pw.fwd_front = ready_ws + n_ct;
+  if (stash_bf16) {
+    if (v == V_PLAIN) return launch_pwfwd<MODE_FWDS, V_PLAIN>(ta, tb, a, pw, n_pw, pairs, st);
+    return launch_pwfwd<MODE_FWDS, V_MV>(ta, tb, a, pw, n_pw, pairs, st);
+  }
+  if (v == V_PLAIN) return launch_pwfwd<MODE_FWD, V_PLAIN>(ta, tb, a, pw, n_pw, pairs, st);
+  if (v == V_MV) return launch_pwfwd<MODE_FWD, V_MV>(ta, tb, a, pw, n_pw, pairs, st);
+  return launch_pwfwd<MODE_FWD, V_SPHERE>(ta, tb, a, pw, n_pw, pairs, st);
 }

@@ -73,6 +73,11 @@ def _merged_bwd() -> bool:
     return os.environ.get("MH_BWD_MERGED", "1") != "0"
 
 
+def _merged_fwd() -> bool:
+    """MH_FWD_MERGED=1 selects the merged W prologue + forward kernel (mh_tc_forward_pw) where head and shape are eligible."""
+    return os.environ.get("MH_FWD_MERGED", "0") == "1"
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -368,7 +373,7 @@ class HeadEngine:
         dev = x.device
         Cn = self.C
         stash = bool(want_grad and self._stash_ok_cached())
-        key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj(), _merged_bwd())
+        key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj(), _merged_bwd(), _merged_fwd())
         if self._step_key != key:
             lib = L.load()
             n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
@@ -383,6 +388,8 @@ class HeadEngine:
                 merge_scratch=b("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev),
                 stats=b("stats", (L.ST_PLANES, B_pad), torch.float32, dev),
                 rowout=b("rowout", (L.RO_PLANES, B_pad), torch.float32, dev))
+            if _merged_fwd() and self.layout == L.LAYOUT_CD:
+                T.update(pw_ready=b("pw_ready", (C_pad // L.NTILE + 1,), torch.int32, dev))
             part_splits = 0
             if want_grad:
                 ns = C.c_int(0)

@@ -140,7 +140,8 @@ int mh_sgd_step_w(float* W, int layout, int64_t C, int64_t ld, const float* grad
  * cosine gather (criterion.py:417,552).  labels are GLOBAL class ids (int64); this shard owns
  * [c_offset, c_offset + C).  Outputs: x_hat bf16 [B_pad,512] (rows >= B zeroed), x_hat32 fp32
  * [B,512], xnorm[B], t_raw[B] = <x_hat_i, w_hat_{y_i}> in fp32 (0 when the label is not owned),
- * label_local[B_pad] (int32; -1 when not owned or row >= B).  c_total = class count of the WHOLE head (= C when
+ * label_local[B_pad] (int32; -1 when not owned or row >= B).  inv_norm may be NULL for the [C, 512] layout: 1/|w_y| is
+ * then taken from the gathered row itself (same arithmetic as mh_prologue_w).  c_total = class count of the WHOLE head (= C when
  * unsharded): a label outside [0, c_total) sets t_raw to NaN so that the loss is NaN on every rank (NaN survives the
  * all-reduce of t_raw; the reference's one_hot.scatter_ fails on such a label, criterion.py:290-291). */
 int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pad, const int64_t* labels,
@@ -187,6 +188,19 @@ int mh_tc_stash_ok(const mh_config* cfg_host, int64_t C);
 int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                   const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                   const int32_t* label_local, const float* state, float* stats_tiles, void* stash_bf16, void* stream);
+
+/* Merged W prologue + forward (optional, [C, 512] parameters: ArcFace, SphereFace, MV-Softmax): mh_prologue_w as a ROLE of
+ * the forward launch.  A few CTA pairs normalise the class centres tile by tile (fp32 W -> bf16 w_hat + inv_norm, bits
+ * identical to mh_prologue_w), the other pairs run mh_tc_forward's kernel and pick every w_hat tile up from L2 right after
+ * it was written: the HBM-bound prologue disappears under the tensor-bound forward and the forward's read of w_hat never
+ * reaches DRAM.  Outputs as mh_prologue_w + mh_tc_forward together.  mh_prologue_x / mh_row_params must have run before
+ * (mh_prologue_x with inv_norm == NULL, since inv_norm is an OUTPUT here).
+ * Query: x_hat_bf16 == NULL writes 1 / 0 to *eligible_host (needs >= 8 class tiles per CTA pair, one launch of row tiles);
+ * when 0, call mh_prologue_w and mh_tc_forward instead.  ready_ws: [C_pad / 256 + 1] ints of scratch (zeroed here). */
+int mh_tc_forward_pw(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const float* W,
+                     int layout, int64_t ld, void* w_hat_bf16, float* inv_norm, int64_t C, int64_t C_pad,
+                     const float* rowp, int64_t ldp, const int32_t* label_local, const float* state,
+                     float* stats_tiles, void* stash_bf16, int* ready_ws, int* eligible_host, void* stream);
 
 /* Recompute backward, step 1: recompute the logit tiles and write G = (P - Y) * dz/dcos as bf16 (never the logits), in the
  * same class-tiled layout as the stash, so each 128-class slab of all rows is one contiguous block (DRAM-page friendly
@@ -369,6 +383,8 @@ typedef struct mh_step_ws {
   float* rpart;                /* [4, C_pad] or NULL */
   int32_t* rflag;              /* [C_pad / 128] or NULL */
   int32_t* dx_sync;            /* [MH_DX_SYNC_INTS] or NULL */
+  int32_t* pw_ready;           /* [C_pad / 256 + 1] or NULL; non-NULL selects the merged prologue + forward kernel
+                                  (mh_tc_forward_pw) whenever the W prologue has to run and the head / shape is eligible */
   int32_t* prog;               /* [2] or NULL; non-NULL (with rpart / rflag) selects the merged dx + dW kernel
                                   (mh_tc_backward_dxdw) whenever both gradients are wanted and the shape is eligible */
 } mh_step_ws;

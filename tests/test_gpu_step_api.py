@@ -89,3 +89,27 @@ def test_merged_dx_dw_kernel_matches_oracle(fam, bmode, B, monkeypatch):
     monkeypatch.setenv("MH_BWD_MERGED", "0")
     base = _run(fam, bmode, B, Cn)
     assert rel(dW, base[4]) < 2e-3 and rel(dx, base[3]) < 1e-4
+
+
+@pytest.mark.parametrize("fam,bmode,B", [("arcface", "auto", 300), ("arcface", "recompute", 1024), ("mv_am", "auto", 700),
+                                         ("sphereface", "auto", 300)])
+def test_merged_prologue_forward_kernel(fam, bmode, B, monkeypatch):
+    """MH_FWD_MERGED=1: the W prologue as a role of the forward launch ([C, 512] heads).  w^ / inv_norm must carry the same
+    bits as the stand-alone prologue, the step the same results as the two-kernel path, and the oracle's within the bar."""
+    import face_recognition_models_b200 as pkg
+    from oracle import margin_oracle as mo
+    from tests.helpers import cosim, rel
+    Cn = 160_001
+    monkeypatch.setenv("MH_FWD_MERGED", "1")
+    loss, a1, a5, dx, dW, (cfg, x, W, labels, margins) = _run(fam, bmode, B, Cn)
+    ref = mo.loss_and_grads(cfg, mo.HeadState(), x, W, labels, margins=margins, lambda_g=0.5)
+    assert abs(float(loss) - float(ref["loss_id"])) < 2e-3 * abs(float(ref["loss_id"]))
+    assert abs(float(a1) - float(ref["acc1"])) < 0.6
+    assert cosim(dx, ref["dx"]) > 0.9995 and cosim(dW, ref["dW"]) > 0.9995
+    again = _run(fam, bmode, B, Cn)
+    assert torch.equal(loss, again[0]) and torch.equal(dx, again[3])
+    monkeypatch.setenv("MH_FWD_MERGED", "0")
+    base = _run(fam, bmode, B, Cn)
+    assert abs(float(loss) - float(base[0])) <= 1e-6 * abs(float(base[0]))
+    assert torch.equal(a1, base[1]) and torch.equal(a5, base[2])
+    assert rel(dx, base[3]) < 1e-5 and rel(dW, base[4]) < 1e-5

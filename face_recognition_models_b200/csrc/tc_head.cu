@@ -1217,31 +1217,73 @@ struct PwArgs {
   const int* fwd_front;
 };
 
-// one warp normalises 4 consecutive classes per step (16 float4 loads in flight per lane); same arithmetic, same
-// summation order as prologue_w_cd_kernel (prologue.cu), so w^ and inv_norm are bit-identical to the stand-alone prologue
-__device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta) {
+// 1-D bulk async copy global -> shared (this CTA), completing on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// Prologue role.  One warp normalises PW_G = 8 consecutive classes per step; the fp32 rows arrive by bulk async copies
+// into a per-warp double-buffered shared-memory slot (2 x 16 KB per warp, 12 warps: 192 KB... capped by PW_SLOT), so the
+// loads of the next step are in flight while this step computes, stores and publishes - the release that publishes a
+// step (it has to wait for the step's stores) never stalls the load stream.  Same arithmetic and summation order as
+// prologue_w_cd_kernel (prologue.cu): w^ and inv_norm are bit-identical to the stand-alone prologue.
+constexpr int PW_G = 4;                              // classes per warp step
+constexpr int PW_SLOT = PW_G * MH_D * 4;             // 8 KB of fp32 rows
+constexpr int PW_WARPS = NUM_THREADS / 32;
+static_assert(2 * PW_WARPS * PW_SLOT + 1024 <= 200 * 1024, "prologue-role staging must fit in shared memory");
+
+__device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint8_t* smem_raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int WARPS = NUM_THREADS / 32;
-  const int64_t groups = p.C_pad / 4;
-  for (int64_t g = (int64_t)cta * WARPS + warp; g < groups; g += (int64_t)ncta * WARPS) {
-    const int64_t row0 = g * 4;
-    const int tile = (int)(row0 / BN);
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t slots = base + 256;                                     // [PW_WARPS][2][PW_SLOT]
+  const uint32_t bar0 = base + warp * 16;                                // two mbarriers per warp
+  uint8_t* slots_ptr = smem_raw + (slots - smem_u32(smem_raw));
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const int64_t groups = p.C_pad / PW_G;
+  const int64_t stride = (int64_t)ncta * PW_WARPS;
+  const bool rows_contig = (p.ld == MH_D);
+  auto issue = [&](int64_t g, int slot) {            // lane 0: start the copies of group g into `slot`
+    const int64_t row0 = g * PW_G;
+    const int64_t nvalid = p.C - row0 < PW_G ? (p.C - row0 < 0 ? 0 : p.C - row0) : PW_G;
+    const uint32_t bar = bar0 + 8 * slot;
+    const uint32_t dst = slots + (uint32_t)((warp * 2 + slot) * PW_SLOT);
+    mbar_expect_tx(bar, (uint32_t)(nvalid * MH_D * 4));
+    if (nvalid == 0) return;
+    if (rows_contig) {
+      bulk_load_1d(dst, p.W + row0 * p.ld, (uint32_t)(nvalid * MH_D * 4), bar);
+    } else {
+      for (int r = 0; r < nvalid; ++r) bulk_load_1d(dst + r * MH_D * 4, p.W + (row0 + r) * p.ld, MH_D * 4, bar);
+    }
+  };
+  int64_t g = (int64_t)cta * PW_WARPS + warp;
+  uint32_t ph[2] = {0u, 0u};
+  int slot = 0;
+  auto throttle = [&](int64_t gg) {                   // stay at most PW_AHEAD class tiles ahead of the forward front
+    const int tile = (int)(gg * PW_G / BN);
     if (tile > ld_acquire_gpu(p.fwd_front) + PW_AHEAD) {
       const long long t0 = clock64();
       while (tile > ld_acquire_gpu(p.fwd_front) + PW_AHEAD) {
         if (clock64() - t0 > 4000000000LL) __trap();
       }
     }
-    float4 v[4][4];
+  };
+  if (g < groups && lane == 0) { throttle(g); issue(g, 0); }
+  for (; g < groups; g += stride) {
+    const int64_t gn = g + stride;
+    if (gn < groups && lane == 0) { throttle(gn); issue(gn, slot ^ 1); }
+    mbar_wait(bar0 + 8 * slot, ph[slot]);
+    ph[slot] ^= 1u;
+    const float4* src = reinterpret_cast<const float4*>(slots_ptr + (warp * 2 + slot) * PW_SLOT);
+    const int64_t row0 = g * PW_G;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t row = row0 + r;
-      const float4* src = reinterpret_cast<const float4*>(p.W + row * p.ld);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[r][k] = (row < p.C) ? __ldg(src + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < PW_G; ++r) {
       const int64_t row = row0 + r;
       uint2* dst = reinterpret_cast<uint2*>(p.what + row * MH_D);
       if (row >= p.C) {
@@ -1249,16 +1291,18 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta) {
         for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = make_uint2(0u, 0u);
         continue;
       }
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = src[r * (MH_D / 4) + lane + 32 * k];
       float ss = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        ss += v[r][k].x * v[r][k].x + v[r][k].y * v[r][k].y + v[r][k].z * v[r][k].z + v[r][k].w * v[r][k].w;
+      for (int k = 0; k < 4; ++k) ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
       ss = warp_sum(ss);
       const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
       if (lane == 0) p.inv_norm[row] = inv;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 o = make_float4(v[r][k].x * inv, v[r][k].y * inv, v[r][k].z * inv, v[r][k].w * inv);
+        const float4 o = make_float4(v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv);
         __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&p0);
@@ -1266,9 +1310,10 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta) {
         dst[lane + 32 * k] = pk;
       }
     }
-    __threadfence();
+    // publish: every lane's stores are ordered before lane 0's release by the warp barrier (cumulativity)
     __syncwarp();
-    if (lane == 0) red_release_gpu_add(p.ready + tile, 4);
+    if (lane == 0) red_release_gpu_add(p.ready + (int)(row0 / BN), PW_G);
+    slot ^= 1;
   }
 }
 
@@ -1278,7 +1323,7 @@ tc_kernel_pwfwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ TcArgs a, const PwArgs pw, const int n_pw) {
   extern __shared__ uint8_t smem_raw[];
   const int64_t pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
-  if (pair < n_pw) pw_role(pw, (int)blockIdx.x, 2 * n_pw);
+  if (pair < n_pw) pw_role(pw, (int)blockIdx.x, 2 * n_pw, smem_raw);
   else tc_body<MODE, V>(tmA, tmB, a, pair - n_pw, pairs - n_pw, smem_raw);
 }
 

@@ -179,6 +179,9 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v) {
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -1232,6 +1235,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 constexpr int PW_G = 4;                              // classes per warp step
 constexpr int PW_SLOT = PW_G * MH_D * 4;             // 8 KB of fp32 rows
 constexpr int PW_WARPS = NUM_THREADS / 32;
+constexpr int PW_BATCH = 4;                          // warp steps per publish
 static_assert(2 * PW_WARPS * PW_SLOT + 1024 <= 200 * 1024, "prologue-role staging must fit in shared memory");
 
 __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint8_t* smem_raw) {
@@ -1263,6 +1267,7 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint
     }
   };
   int64_t g = (int64_t)cta * PW_WARPS + warp;
+  int pend[PW_BATCH], npend = 0;
   uint32_t ph[2] = {0u, 0u};
   int slot = 0;
   auto throttle = [&](int64_t gg) {                   // stay at most PW_AHEAD class tiles ahead of the forward front
@@ -1310,10 +1315,24 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint
         dst[lane + 32 * k] = pk;
       }
     }
-    // publish: every lane's stores are ordered before lane 0's release by the warp barrier (cumulativity)
-    __syncwarp();
-    if (lane == 0) red_release_gpu_add(p.ready + (int)(row0 / BN), PW_G);
+    // publish every PW_BATCH steps: one release fence (it waits for the steps' stores to be performed) covers them all;
+    // every lane's stores are ordered before lane 0's fence by the warp barrier (cumulativity)
+    pend[npend++] = (int)(row0 / BN);
+    if (npend == PW_BATCH) {
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < PW_BATCH; ++i) red_relaxed_gpu_add(p.ready + pend[i], PW_G);
+      }
+      npend = 0;
+    }
     slot ^= 1;
+  }
+  __syncwarp();
+  if (lane == 0 && npend > 0) {
+    __threadfence();
+    for (int i = 0; i < npend; ++i) red_relaxed_gpu_add(p.ready + pend[i], PW_G);
   }
 }
 

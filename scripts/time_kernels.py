@@ -41,7 +41,7 @@ def measure(tag):
 settings = [dict(kv.split("=") for kv in grp.split(",") if kv) for grp in os.environ.get("SETTINGS", "").split(";")]
 for rep in range(int(os.environ.get("REPS", 2))):
     for st in settings:
-        for k in [k for k in os.environ if k.startswith("MH_") and k not in ("MH_LIB", "MH_DXDW_FRAC", "MH_PROG_AHEAD")]:
+        for k in [k for k in os.environ if k.startswith("MH_") and k not in ("MH_LIB", "MH_DXDW_FRAC", "MH_PROG_AHEAD", "MH_PW_PAIRS")]:
             os.environ.pop(k, None)      # experiment toggles are per setting
         head.backward_mode = "auto"
         for k, v in st.items():

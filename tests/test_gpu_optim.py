@@ -190,3 +190,35 @@ def test_error_paths():
     cpu_head.weight.grad = torch.zeros_like(cpu_head.weight)
     with pytest.raises(L.MarginHeadError):
         opt.step()
+
+
+def test_coupled_found_inf_skips_the_head_step_too():
+    """GradScaler decides the inf-skip per optimizer.  With coupled=[opt_backbone] + couple_scaler(scaler) an
+    overflow seen only in the BACKBONE gradients also skips the head update (what the reference's single optimizer does),
+    without a host sync; without the coupling the head would step."""
+    import face_recognition_models_b200 as pkg
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(512, 512).cuda()                              # stands in for the backbone
+    x = torch.randn(32, 512, device="cuda")
+    y = torch.randint(0, 1000, (32,), device="cuda")
+    for coupled in (True, False):
+        head = pkg.ArcFace(512, 1000, s=64.0, m=0.5, easy_margin=False).cuda()
+        opt_b = torch.optim.SGD(lin.parameters(), lr=0.01, momentum=0.9)
+        opt_h = pkg.HeadSGD([head], lr=0.05, momentum=0.9, weight_decay=5e-4, coupled=[opt_b] if coupled else ())
+        scaler = torch.amp.GradScaler("cuda", init_scale=256.0)
+        if coupled:
+            opt_h.couple_scaler(scaler)
+        w0 = head.weight.detach().clone()
+        opt_b.zero_grad(set_to_none=True)
+        opt_h.zero_grad(set_to_none=True)
+        out = head.fused_loss(lin(x), y)
+        scaler.scale(out.loss).backward()
+        lin.weight.grad[0, 0] = float("inf")                            # overflow in the backbone gradients only
+        assert bool(torch.isfinite(head.weight.grad).all())
+        scaler.unscale_(opt_b)                                           # records opt_b's found_inf (must precede the head step)
+        scaler.step(opt_b)
+        scaler.step(opt_h)
+        scaler.update()
+        moved = not torch.equal(head.weight.detach(), w0)
+        assert moved == (not coupled), (coupled, moved)
+        assert float(scaler.get_scale()) == 128.0                        # the overflow halves the scale either way

@@ -1210,7 +1210,7 @@ tc_kernel_dxdw(const __grid_constant__ CUtensorMap tmA_dx, const __grid_constant
 // (red.release after the rows' stores; the forward producer acquires it, then fence.proxy.async before its TMA loads);
 // the prologue role stays at most PW_AHEAD tiles ahead of the forward front (L2 residency), and only the role that is
 // ahead ever waits.  Bounded spins, all CTAs resident (grid = #SMs).
-constexpr int PW_AHEAD = 64;
+constexpr int PW_AHEAD = 96;
 struct PwArgs {
   const float* W;
   int64_t C, C_pad, ld;
@@ -1270,13 +1270,18 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint
   int pend[PW_BATCH], npend = 0;
   uint32_t ph[2] = {0u, 0u};
   int slot = 0;
-  auto throttle = [&](int64_t gg) {                   // stay at most PW_AHEAD class tiles ahead of the forward front
+  // stay at most PW_AHEAD class tiles ahead of the forward front.  The front is re-read only when the cached value says
+  // "too far ahead" or every 8th step (a global load per step in lane 0's issue path cost more than the copies)
+  int front = 0, since = 8;
+  auto throttle = [&](int64_t gg) {
     const int tile = (int)(gg * PW_G / BN);
-    if (tile > ld_acquire_gpu(p.fwd_front) + PW_AHEAD) {
+    if (++since >= 8) { front = ld_acquire_gpu(p.fwd_front); since = 0; }
+    if (tile > front + PW_AHEAD) {
       const long long t0 = clock64();
-      while (tile > ld_acquire_gpu(p.fwd_front) + PW_AHEAD) {
+      while (tile > (front = ld_acquire_gpu(p.fwd_front)) + PW_AHEAD) {
         if (clock64() - t0 > 4000000000LL) __trap();
       }
+      since = 0;
     }
   };
   if (g < groups && lane == 0) { throttle(g); issue(g, 0); }

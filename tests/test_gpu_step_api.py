@@ -113,3 +113,32 @@ def test_merged_prologue_forward_kernel(fam, bmode, B, monkeypatch):
     assert abs(float(loss) - float(base[0])) <= 1e-6 * abs(float(base[0]))
     assert torch.equal(a1, base[1]) and torch.equal(a5, base[2])
     assert rel(dx, base[3]) < 1e-5 and rel(dW, base[4]) < 1e-5
+
+
+@pytest.mark.parametrize("B", [2048, 4096, 8192])
+def test_merged_backward_at_multi_gpu_row_counts(B):
+    """The per-rank shapes of the class-sharded head at 2 / 4 / 8 GPUs (B_g = 2048 / 4096 / 8192 rows: 8 / 16 / 32 row tiles,
+    dx role split 4 / 2 / 1) through the merged dx + dW kernel on one GPU, against the chunked fp32 restatement."""
+    import face_recognition_models_b200 as pkg
+    from oracle.chunked_fp32 import chunked_reference, cosine
+    Cn = 160_001
+    g = torch.Generator(device="cuda").manual_seed(B)
+    head = pkg.ArcFace(512, Cn, s=64.0, m=0.5, easy_margin=False).cuda()
+    with torch.no_grad():
+        head.weight.normal_(0, 0.01, generator=g)
+    y = torch.randint(0, Cn, (B,), device="cuda", generator=g)
+    x = torch.randn(B, 512, device="cuda", generator=g)
+    near = torch.arange(B, device="cuda") % 2 == 0
+    with torch.no_grad():
+        x[near] = 20.0 * torch.nn.functional.normalize(
+            torch.nn.functional.normalize(head.weight[y[near]], dim=1) + torch.nn.functional.normalize(x[near], dim=1), dim=1)
+    x.requires_grad_(True)
+    out = head.fused_loss(x, y)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        loss, dx, dW = chunked_reference(x.detach(), head.weight.detach(), y, "arcface", 64.0, 0.5, chunk=20_000)
+    assert abs(float(out.loss) - float(loss)) <= 2e-3 * abs(float(loss))
+    assert cosine(x.grad, dx) >= 0.9995 and cosine(head.weight.grad, dW) >= 0.9995
+    assert abs(float(x.grad.norm()) / float(dx.norm()) - 1.0) <= 2e-3
+    assert abs(float(head.weight.grad.norm()) / float(dW.norm()) - 1.0) <= 2e-3

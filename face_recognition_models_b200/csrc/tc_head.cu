@@ -1220,17 +1220,10 @@ struct PwArgs {
   const int* fwd_front;
 };
 
-// 1-D bulk async copy global -> shared (this CTA), completing on an mbarrier of this CTA
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-// Prologue role.  One warp normalises PW_G = 8 consecutive classes per step; the fp32 rows arrive by bulk async copies
-// into a per-warp double-buffered shared-memory slot (2 x 16 KB per warp, 12 warps: 192 KB... capped by PW_SLOT), so the
-// loads of the next step are in flight while this step computes, stores and publishes - the release that publishes a
-// step (it has to wait for the step's stores) never stalls the load stream.  Same arithmetic and summation order as
+// Prologue role.  One warp normalises PW_G = 4 consecutive classes per step; the fp32 rows arrive by TMA into a per-warp
+// double-buffered shared-memory slot (2 x 8 KB per warp, 12 warps: 192 KB), so the loads of the next step are in flight
+// while this step computes, stores and publishes - the release fence that publishes (it has to wait for the stores) never
+// stalls the load stream.  Same arithmetic and summation order as
 // prologue_w_cd_kernel (prologue.cu): w^ and inv_norm are bit-identical to the stand-alone prologue.
 constexpr int PW_G = 4;                              // classes per warp step
 constexpr int PW_SLOT = PW_G * MH_D * 4;             // 8 KB of fp32 rows
@@ -1238,7 +1231,7 @@ constexpr int PW_WARPS = NUM_THREADS / 32;
 constexpr int PW_BATCH = 4;                          // warp steps per publish
 static_assert(2 * PW_WARPS * PW_SLOT + 1024 <= 200 * 1024, "prologue-role staging must fit in shared memory");
 
-__device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint8_t* smem_raw) {
+__device__ __forceinline__ void pw_role(const PwArgs& p, const CUtensorMap* tmW32, int cta, int ncta, uint8_t* smem_raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t slots = base + 256;                                     // [PW_WARPS][2][PW_SLOT]
@@ -1252,19 +1245,15 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint
   __syncwarp();
   const int64_t groups = p.C_pad / PW_G;
   const int64_t stride = (int64_t)ncta * PW_WARPS;
-  const bool rows_contig = (p.ld == MH_D);
+  // the fp32 rows arrive by 2-D TMA (the tensor engine's tiled path; 1-D bulk copies sustained only ~30 GB/s per SM):
+  // two boxes of [PW_G rows][256 columns] per group, rows beyond C read as zeros (out-of-bounds fill)
   auto issue = [&](int64_t g, int slot) {            // lane 0: start the copies of group g into `slot`
-    const int64_t row0 = g * PW_G;
-    const int64_t nvalid = p.C - row0 < PW_G ? (p.C - row0 < 0 ? 0 : p.C - row0) : PW_G;
+    const int row0 = (int)(g * PW_G);
     const uint32_t bar = bar0 + 8 * slot;
     const uint32_t dst = slots + (uint32_t)((warp * 2 + slot) * PW_SLOT);
-    mbar_expect_tx(bar, (uint32_t)(nvalid * MH_D * 4));
-    if (nvalid == 0) return;
-    if (rows_contig) {
-      bulk_load_1d(dst, p.W + row0 * p.ld, (uint32_t)(nvalid * MH_D * 4), bar);
-    } else {
-      for (int r = 0; r < nvalid; ++r) bulk_load_1d(dst + r * MH_D * 4, p.W + (row0 + r) * p.ld, MH_D * 4, bar);
-    }
+    mbar_expect_tx(bar, PW_SLOT);
+    tma_load_2d_local(dst, tmW32, bar, 0, row0);
+    tma_load_2d_local(dst + PW_SLOT / 2, tmW32, bar, 256, row0);
   };
   int64_t g = (int64_t)cta * PW_WARPS + warp;
   int pend[PW_BATCH], npend = 0;
@@ -1303,7 +1292,7 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint
       }
       float4 v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = src[r * (MH_D / 4) + lane + 32 * k];
+      for (int k = 0; k < 4; ++k) v[k] = src[(k >> 1) * (PW_SLOT / 32) + r * 64 + lane + 32 * (k & 1)];
       float ss = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
@@ -1344,10 +1333,10 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, int cta, int ncta, uint
 template <int MODE, int V>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel_pwfwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ TcArgs a, const PwArgs pw, const int n_pw) {
+                const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmW32, const PwArgs pw, const int n_pw) {
   extern __shared__ uint8_t smem_raw[];
   const int64_t pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
-  if (pair < n_pw) pw_role(pw, (int)blockIdx.x, 2 * n_pw, smem_raw);
+  if (pair < n_pw) pw_role(pw, &tmW32, (int)blockIdx.x, 2 * n_pw, smem_raw);
   else tc_body<MODE, V>(tmA, tmB, a, pair - n_pw, pairs - n_pw, smem_raw);
 }
 
@@ -1802,9 +1791,24 @@ extern "C" int mh_tc_backward_dxdw(const void* G_bf16, int64_t B_pad, int64_t C,
 }
 
 // ---- merged W prologue + forward: host side ------------------------------------------------------------------------
+// fp32 [rows][512] row-major (pitch ld floats), boxes of [PW_G rows][256 columns], no swizzle, zero fill out of bounds
+static int make_tmap_w32(CUtensorMap* out, const float* base, int64_t rows, int64_t ld) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { mh_set_error("cuTensorMapEncodeTiled entry point not found"); return MH_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)MH_D, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {256u, (cuuint32_t)PW_G};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mh_set_error("cuTensorMapEncodeTiled (fp32 W) failed with CUresult %d", (int)r); return MH_ERR_CUDA; }
+  return MH_OK;
+}
+
 template <int MODE, int V>
-static int launch_pwfwd(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, const PwArgs& pw, int n_pw,
-                        int pairs, cudaStream_t st) {
+static int launch_pwfwd(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, const CUtensorMap& tw32,
+                        const PwArgs& pw, int n_pw, int pairs, cudaStream_t st) {
   static MhDeviceOnce attr_once;
   constexpr int smem = mode_smem_bytes(MODE);
   MH_CUDA_OK(mh_once_per_device(attr_once, [&] {
@@ -1822,7 +1826,7 @@ static int launch_pwfwd(const CUtensorMap& ta, const CUtensorMap& tb, const TcAr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel_pwfwd<MODE, V>, ta, tb, args, pw, n_pw));
+  MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel_pwfwd<MODE, V>, ta, tb, args, tw32, pw, n_pw));
   return MH_OK;
 }
 
@@ -1884,11 +1888,13 @@ extern "C" int mh_tc_forward_pw(const mh_config* cfg_host, const void* x_hat_bf1
   PwArgs pw{};
   pw.W = W; pw.C = C; pw.C_pad = C_pad; pw.ld = ld;
   pw.what = (__nv_bfloat16*)w_hat_bf16; pw.inv_norm = inv_norm; pw.ready = ready_ws; pw.fwd_front = ready_ws + n_ct;
+  CUtensorMap tw32;
+  if (int e = make_tmap_w32(&tw32, W, C, ld)) return e;
   if (stash_bf16) {
-    if (v == V_PLAIN) return launch_pwfwd<MODE_FWDS, V_PLAIN>(ta, tb, a, pw, n_pw, pairs, st);
-    return launch_pwfwd<MODE_FWDS, V_MV>(ta, tb, a, pw, n_pw, pairs, st);
+    if (v == V_PLAIN) return launch_pwfwd<MODE_FWDS, V_PLAIN>(ta, tb, a, tw32, pw, n_pw, pairs, st);
+    return launch_pwfwd<MODE_FWDS, V_MV>(ta, tb, a, tw32, pw, n_pw, pairs, st);
   }
-  if (v == V_PLAIN) return launch_pwfwd<MODE_FWD, V_PLAIN>(ta, tb, a, pw, n_pw, pairs, st);
-  if (v == V_MV) return launch_pwfwd<MODE_FWD, V_MV>(ta, tb, a, pw, n_pw, pairs, st);
-  return launch_pwfwd<MODE_FWD, V_SPHERE>(ta, tb, a, pw, n_pw, pairs, st);
+  if (v == V_PLAIN) return launch_pwfwd<MODE_FWD, V_PLAIN>(ta, tb, a, tw32, pw, n_pw, pairs, st);
+  if (v == V_MV) return launch_pwfwd<MODE_FWD, V_MV>(ta, tb, a, tw32, pw, n_pw, pairs, st);
+  return launch_pwfwd<MODE_FWD, V_SPHERE>(ta, tb, a, tw32, pw, n_pw, pairs, st);
 }

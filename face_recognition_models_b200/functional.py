@@ -34,7 +34,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # the raw cudaStream_t of the current stream of the current device (the engine methods run under the data's device);
+    # torch.cuda.current_stream() builds a Stream object through several Python layers: ~20 us per call on the hot path
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _on_device_of(argpos: int, same_device=(0, 1, 2, 3)):

@@ -1281,27 +1281,35 @@ __device__ __forceinline__ void pw_role(const PwArgs& p, const CUtensorMap* tmW3
     ph[slot] ^= 1u;
     const float4* src = reinterpret_cast<const float4*>(slots_ptr + (warp * 2 + slot) * PW_SLOT);
     const int64_t row0 = g * PW_G;
+    // the PW_G classes of a step are independent: keep their dependency chains (square sums, warp reductions, the
+    // reciprocal) interleaved - with 12 warps per SM the role is latency-bound, not bandwidth-bound, otherwise
+    float4 v[PW_G][4];
+    float ss[PW_G], inv[PW_G];
+#pragma unroll
+    for (int r = 0; r < PW_G; ++r) {
+      ss[r] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[r][k] = src[(k >> 1) * (PW_SLOT / 32) + r * 64 + lane + 32 * (k & 1)];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int r = 0; r < PW_G; ++r)
+        ss[r] += v[r][k].x * v[r][k].x + v[r][k].y * v[r][k].y + v[r][k].z * v[r][k].z + v[r][k].w * v[r][k].w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < PW_G; ++r) ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);
+#pragma unroll
+    for (int r = 0; r < PW_G; ++r) inv[r] = 1.f / fmaxf(sqrtf(ss[r]), 1e-12f);
 #pragma unroll
     for (int r = 0; r < PW_G; ++r) {
       const int64_t row = row0 + r;
       uint2* dst = reinterpret_cast<uint2*>(p.what + row * MH_D);
-      if (row >= p.C) {
+      if (lane == 0 && row < p.C) p.inv_norm[row] = inv[r];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[lane + 32 * k] = make_uint2(0u, 0u);
-        continue;
-      }
-      float4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = src[(k >> 1) * (PW_SLOT / 32) + r * 64 + lane + 32 * (k & 1)];
-      float ss = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
-      ss = warp_sum(ss);
-      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-      if (lane == 0) p.inv_norm[row] = inv;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 o = make_float4(v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv);
+      for (int k = 0; k < 4; ++k) {                  // rows >= C arrive as zeros (TMA out-of-bounds fill) and stay zero
+        const float4 o = make_float4(v[r][k].x * inv[r], v[r][k].y * inv[r], v[r][k].z * inv[r], v[r][k].w * inv[r]);
         __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&p0);

@@ -132,6 +132,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// Long waits (the dx epilogue warps wait ~1 ms for a whole split-K accumulation): back off with nanosleep instead of
+// re-issuing try_wait at full rate - fewer wasted issue slots next to the MMA / producer warps, same wake-up within 1 us.
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned ns = 64;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    ns = ns < 1024 ? ns * 2 : 1024;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // TMA load into this CTA's shared memory, completing on this CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_local(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -762,6 +774,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
           if (ct > ld_acquire_gpu(a.prog) + a.prog_ahead) {
             const long long t0 = clock64();
             while (ct > ld_acquire_gpu(a.prog) + a.prog_ahead) {
+              __nanosleep(256);
               if (clock64() - t0 > 4000000000LL) __trap();
             }
           }
@@ -773,6 +786,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
             if (ct > ld_acquire_gpu(a.prog + 1) + a.prog_ahead) {
               const long long t0 = clock64();
               while (ct > ld_acquire_gpu(a.prog + 1) + a.prog_ahead) {
+                __nanosleep(256);
                 if (clock64() - t0 > 4000000000LL) __trap();
               }
             }
@@ -1049,7 +1063,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
             if (++side_stage == STAGES) { side_stage = 0; side_phase ^= 1; }
           }
         }
-        mbar_wait(bar_tfull + 8 * buf, bphase);
+        mbar_wait_long(bar_tfull + 8 * buf, bphase);
         tc_fence_after();
         chunk_loop<NCHUNK>(taddr, [&](int c, uint32_t (&cur)[32]) {
           float* dst = a.out + (int64_t)w.split * a.out_split_stride + row * MH_D + cbase + c * 32;

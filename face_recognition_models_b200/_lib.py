@@ -38,7 +38,7 @@ class MhStepWs(C.Structure):
         ("rowout", C.c_void_p), ("bc", C.c_void_p), ("xs", C.c_void_p), ("rho", C.c_void_p), ("gty", C.c_void_p),
         ("dxhat_part", C.c_void_p), ("part_splits", C.c_int64), ("dxhat_full", C.c_void_p), ("gscal", C.c_void_p),
         ("r_colsum", C.c_void_p), ("rpart", C.c_void_p), ("rflag", C.c_void_p), ("dx_sync", C.c_void_p),
-        ("pw_ready", C.c_void_p), ("prog", C.c_void_p),
+        ("pw_ready", C.c_void_p), ("prog", C.c_void_p), ("guard", C.c_void_p),
     ]
 
 
@@ -83,6 +83,7 @@ SIGNATURES = {
     "mh_step_backward": [_cfgp, C.POINTER(MhStepWs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mh_tc_fixref_ok": [_cfgp, _i64],
     "mh_tc_stash_ok": [_cfgp, _i64],
+    "mh_tc_stash_guarded_ok": [_cfgp, _i64],
     "mh_stash_prep": [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "mh_stash_dx_combine": [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "mh_stash_dw_target": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
@@ -155,10 +156,13 @@ def _launches(name: str, args) -> int:
     if name == "mh_tc_backward_dxdw":
         return 0 if not getattr(args[11], "value", None) else 1
     if name == "mh_step_forward":
-        return 6 + (1 if int(args[8]) else 0)              # x prologue, row terms, identity fill, forward, merge, finalize (+ W prologue)
+        # x prologue, row terms, identity fill, forward, merge, finalize (+ W prologue; + the four gated launches of the
+        # guarded stash's fallback: identity fill, general forward, merge, finalize)
+        return 6 + (1 if int(args[8]) else 0) + (4 if int(args[9]) == 2 else 0)
     if name == "mh_step_backward":
         stash, dx, dw = int(args[2]), bool(getattr(args[6], "value", None)), bool(getattr(args[7], "value", None))
-        return 1 + (1 if stash else 1) + ((3 if stash else 2) if dx else 0) + ((3 if stash else 2) if dw else 0)
+        return (1 + (1 if stash else 1) + ((3 if stash else 2) if dx else 0) + ((3 if stash else 2) if dw else 0)
+                + (1 if stash == 2 else 0))
     return 1
 
 

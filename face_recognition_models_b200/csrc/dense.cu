@@ -230,8 +230,9 @@ extern "C" int mh_dense_backward_dc(const mh_config* cfg_host, float* S, int64_t
 // merge_stats: online-softmax merge over tiles / shards.  grid (rows/128, nblk); block (128, 8).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) merge_stats_kernel(const float* __restrict__ in, int64_t n_parts, int64_t lds_,
-                                                           float* __restrict__ out) {
+                                                           float* __restrict__ out, const int* gate, int gate_on) {
   __shared__ RowStat sh[8][128];
+  if (gate && ((*reinterpret_cast<const volatile int*>(gate) != 0) != (gate_on != 0))) return;   // guarded stash, see mh_step_forward
   const int rx = threadIdx.x, py = threadIdx.y;
   const int64_t row = (int64_t)blockIdx.x * 128 + rx;
   const int64_t per = (n_parts + gridDim.y - 1) / gridDim.y;
@@ -258,6 +259,11 @@ __global__ void __launch_bounds__(1024) merge_stats_kernel(const float* __restri
 
 extern "C" int mh_merge_stats(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds_, float* scratch,
                               float* stats_out, void* stream) {
+  return mh_merge_stats_impl(stats_in, n_parts, B, lds_, scratch, stats_out, nullptr, 0, stream);
+}
+
+int mh_merge_stats_impl(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds_, float* scratch, float* stats_out,
+                        const int* gate, int gate_on, void* stream) {
   MH_CHECK_ARG(stats_in && stats_out && n_parts > 0 && lds_ >= B, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 block(128, 8);
@@ -265,10 +271,10 @@ extern "C" int mh_merge_stats(const float* stats_in, int64_t n_parts, int64_t B,
   int64_t nblk = (n_parts >= 256) ? MH_MERGE_BLOCKS : 1;
   if (nblk > 1) {
     MH_CHECK_ARG(scratch, "scratch required for large merges");
-    merge_stats_kernel<<<dim3(gx, (unsigned)nblk), block, 0, st>>>(stats_in, n_parts, lds_, scratch);
-    merge_stats_kernel<<<dim3(gx, 1), block, 0, st>>>(scratch, nblk, lds_, stats_out);
+    merge_stats_kernel<<<dim3(gx, (unsigned)nblk), block, 0, st>>>(stats_in, n_parts, lds_, scratch, gate, gate_on);
+    merge_stats_kernel<<<dim3(gx, 1), block, 0, st>>>(scratch, nblk, lds_, stats_out, gate, gate_on);
   } else {
-    merge_stats_kernel<<<dim3(gx, 1), block, 0, st>>>(stats_in, n_parts, lds_, stats_out);
+    merge_stats_kernel<<<dim3(gx, 1), block, 0, st>>>(stats_in, n_parts, lds_, stats_out, gate, gate_on);
   }
   MH_LAUNCH_OK();
   return MH_OK;
@@ -281,11 +287,17 @@ __global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __rest
                                                              const float* __restrict__ rowp, int64_t ldp, int64_t B,
                                                              int64_t B_total, int sphere, float* __restrict__ rowout,
                                                              int64_t ldo, float* __restrict__ scalars,
-                                                             const float* __restrict__ state) {
+                                                             const float* __restrict__ state, float guard_min_l,
+                                                             int* __restrict__ guard_flag, const int* gate, int gate_on) {
   __shared__ double sh[3][32];
+  if (gate && ((*reinterpret_cast<const volatile int*>(gate) != 0) != (gate_on != 0))) return;   // guarded stash, see mh_step_forward
   double sl = 0.0, s1 = 0.0, s5 = 0.0;
+  int unsafe = 0;
   for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
     const float m = stats[MH_ST_M * lds_ + i], l = stats[MH_ST_L * lds_ + i];
+    // guarded stash: the fixed-reference sums of this row are exact to 2^-24 only if they dwarf everything that can have
+    // been flushed to zero (mh_tc_stash_guarded_ok); written as !(l >= min) so that a NaN row is not "safe" by accident
+    if (guard_flag && !(l >= guard_min_l) && l == l) unsafe = 1;
     const float cnt = stats[MH_ST_CNT * lds_ + i], ez = stats[MH_ST_EZ * lds_ + i];
     const float zt = rowp[MH_RP_ZT * ldp + i], scale = rowp[MH_RP_SCALE * ldp + i];
     const float lse2 = m + log2f(l);
@@ -308,7 +320,12 @@ __global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __rest
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     if (lane == 0) sh[k][w] = v[k];
   }
-  __syncthreads();
+  if (guard_flag) {
+    unsafe = __syncthreads_or(unsafe);
+    if (threadIdx.x == 0) *guard_flag = unsafe ? 1 : 0;
+  } else {
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     double t[3] = {0, 0, 0};
     for (int k = 0; k < 3; ++k)
@@ -323,10 +340,19 @@ __global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __rest
 extern "C" int mh_finalize_rows(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B,
                                 int64_t B_total, int sphere, float* rowout, int64_t ldo, float* scalars,
                                 const float* state, void* stream) {
+  return mh_finalize_rows_impl(stats, lds_, rowp, ldp, B, B_total, sphere, rowout, ldo, scalars, state, 0.f, nullptr,
+                               nullptr, 0, stream);
+}
+
+// guard_flag != NULL: also decide whether the fixed-reference sums can be trusted (every row sum >= guard_min_l) and write
+// 0 / 1 to *guard_flag.  gate: the whole launch is a no-op unless (*gate != 0) == (gate_on != 0).
+int mh_finalize_rows_impl(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B, int64_t B_total,
+                          int sphere, float* rowout, int64_t ldo, float* scalars, const float* state, float guard_min_l,
+                          int* guard_flag, const int* gate, int gate_on, void* stream) {
   MH_CHECK_ARG(stats && rowp && rowout && scalars, "null pointer");
   MH_CHECK_ARG(B > 0 && B_total >= B && lds_ >= B && ldp >= B && ldo >= B, "bad shape");
   finalize_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stats, lds_, rowp, ldp, B, B_total, sphere, rowout, ldo,
-                                                             scalars, state);
+                                                             scalars, state, guard_min_l, guard_flag, gate, gate_on);
   MH_LAUNCH_OK();
   return MH_OK;
 }

@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(256) stash_prep_kernel(const float* __restrict
                                                          const float* __restrict__ rowout, int64_t ldo,
                                                          const float* __restrict__ xhat32, int64_t B, int64_t B_pad,
                                                          float umax, __nv_bfloat16* __restrict__ xs,
-                                                         float* __restrict__ rho, float* __restrict__ gty) {
+                                                         float* __restrict__ rho, float* __restrict__ gty,
+                                                         const int* __restrict__ fallback) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B_pad) return;
@@ -24,12 +25,14 @@ __global__ void __launch_bounds__(256) stash_prep_kernel(const float* __restrict
     if (lane == 0) { rho[row] = 0.f; gty[row] = 0.f; }
     return;
   }
+  // guarded stash, fallback taken (mh_step_backward): the B x C buffer holds the recomputed G itself, target column included
+  const bool fb = fallback != nullptr && *fallback != 0;
   const float scale = rowp[MH_RP_SCALE * ldp + row];
   const float ref2 = scale * MH_LOG2E * umax - 102.f;
-  const float r = scale * exp2f(ref2 - rowout[MH_RO_LSE2 * ldo + row]);
+  const float r = fb ? 1.f : scale * exp2f(ref2 - rowout[MH_RO_LSE2 * ldo + row]);
   if (lane == 0) {
     rho[row] = r;
-    gty[row] = rowout[MH_RO_AUX0 * ldo + row] * rowp[MH_RP_DZT * ldp + row];
+    gty[row] = fb ? 0.f : rowout[MH_RO_AUX0 * ldo + row] * rowp[MH_RP_DZT * ldp + row];
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -45,11 +48,17 @@ __global__ void __launch_bounds__(256) stash_prep_kernel(const float* __restrict
 extern "C" int mh_stash_prep(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
                              const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty,
                              void* stream) {
+  return mh_stash_prep_impl(cfg_host, rowp, ldp, rowout, ldo, x_hat32, B, B_pad, xs_bf16, rho, gty, nullptr, stream);
+}
+
+int mh_stash_prep_impl(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
+                       const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty,
+                       const int* fallback, void* stream) {
   MH_CHECK_ARG(cfg_host && rowp && rowout && x_hat32 && xs_bf16 && rho && gty, "null pointer");
   MH_CHECK_ARG(B > 0 && B_pad >= B && ldp >= B && ldo >= B, "bad shape");
   const MhParams p = mh_make_params(cfg_host);
   stash_prep_kernel<<<(unsigned)((B_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      rowp, ldp, rowout, ldo, x_hat32, B, B_pad, mh_family_umax(&p), (__nv_bfloat16*)xs_bf16, rho, gty);
+      rowp, ldp, rowout, ldo, x_hat32, B, B_pad, mh_family_umax(&p), (__nv_bfloat16*)xs_bf16, rho, gty, fallback);
   MH_LAUNCH_OK();
   return MH_OK;
 }

@@ -27,6 +27,9 @@ extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const
   MH_CHECK_ARG(cfg && x && labels && W && state && scalars, "null pointer");
   STEP_TRY(check_ws(ws));
   MH_CHECK_ARG(!stash || ws->bc, "stash requested without a B x C buffer");
+  MH_CHECK_ARG(stash >= 0 && stash <= 2, "stash must be 0 (none), 1 (proven) or 2 (guarded)");
+  MH_CHECK_ARG(stash != 2 || ws->guard, "the guarded stash needs ws->guard");
+  MH_CHECK_ARG(stash != 2 || !ws->pw_ready, "the guarded stash does not combine with the merged prologue + forward");
   MH_CHECK_ARG(ws->n_tiles == mh_fwd_num_tiles(ws->C_pad), "stats_tiles must hold mh_fwd_num_tiles records");
   // merged prologue + forward (ws->pw_ready set, the W prologue has to run, eligible head / shape): the prologue becomes
   // a role of the forward launch; 1/|w_y| of the target rows is then taken by the x prologue from the gathered rows
@@ -45,11 +48,26 @@ extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const
                               ws->rowp, ws->B_pad, ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr,
                               ws->pw_ready, &pw_ok, stream));
   else
-    STEP_TRY(mh_tc_forward(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
-                           ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr, stream));
+    STEP_TRY(mh_tc_forward_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                                ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr, stash, nullptr, 0, stream));
+  const int sphere = cfg->family == MH_SPHEREFACE ? 1 : 0;
   STEP_TRY(mh_merge_stats(ws->stats_tiles, ws->n_tiles, ws->B, ws->B_pad, ws->merge_scratch, ws->stats, stream));
-  STEP_TRY(mh_finalize_rows(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, cfg->family == MH_SPHEREFACE ? 1 : 0,
-                            ws->rowout, ws->B_pad, scalars, state, stream));
+  if (stash != 2) {
+    STEP_TRY(mh_finalize_rows(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, sphere, ws->rowout, ws->B_pad, scalars,
+                              state, stream));
+    return MH_OK;
+  }
+  // Guarded stash: the finaliser decides on the device whether the speculative fixed-reference sums stand (every row sum
+  // >= C 2^-102, see mh_tc_stash_guarded_ok) and sets ws->guard; the general forward follows as launches gated on it.
+  const float guard_min_l = ldexpf((float)ws->C, -102);
+  STEP_TRY(mh_finalize_rows_impl(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, sphere, ws->rowout, ws->B_pad,
+                                 scalars, state, guard_min_l, ws->guard, nullptr, 0, stream));
+  STEP_TRY(mh_tc_forward_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                              ws->label_local, state, ws->stats_tiles, nullptr, 0, ws->guard, 1, stream));
+  STEP_TRY(mh_merge_stats_impl(ws->stats_tiles, ws->n_tiles, ws->B, ws->B_pad, ws->merge_scratch, ws->stats, ws->guard, 1,
+                               stream));
+  STEP_TRY(mh_finalize_rows_impl(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, sphere, ws->rowout, ws->B_pad,
+                                 scalars, state, 0.f, nullptr, ws->guard, 1, stream));
   return MH_OK;
 }
 
@@ -60,6 +78,9 @@ extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int 
   MH_CHECK_ARG(ws->bc && ws->gscal && ws->dxhat_part, "null backward workspace pointer");
   MH_CHECK_ARG(ws->r_colsum || (ws->rpart && ws->rflag), "need r_colsum (side-pass projection) or rpart + rflag (self-projection)");
   MH_CHECK_ARG(!stash || (ws->xs && ws->rho && ws->gty && ws->dxhat_full), "null stash workspace pointer");
+  MH_CHECK_ARG(stash != 2 || (ws->guard && !ws->r_colsum && ws->rpart && ws->rflag),
+               "the guarded stash needs ws->guard and the self-projecting dW kernel (r_colsum == NULL, rpart, rflag)");
+  const int* fallback = stash == 2 ? ws->guard : nullptr;
   const float* rowout = ws->rowout;
   const float* aux0 = rowout + (int64_t)MH_RO_AUX0 * ws->B_pad;
   const float* aux1 = rowout + (int64_t)MH_RO_AUX1 * ws->B_pad;
@@ -82,8 +103,11 @@ extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int 
   if (merged_split > 0) {
     MH_CHECK_ARG(merged_split <= ws->part_splits, "dxhat_part holds fewer splits than the merged backward needs");
     if (stash) {
-      STEP_TRY(mh_stash_prep(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
-                             ws->gty, stream));
+      if (fallback)      // guarded stash whose forward fell back: rewrite the stash with the recomputed G (no-op otherwise)
+        STEP_TRY(mh_tc_backward_g_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                                       ws->label_local, state, lse2, ws->bc, nullptr, fallback, 1, stream));
+      STEP_TRY(mh_stash_prep_impl(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
+                                  ws->gty, fallback, stream));
       xs = ws->xs;
     } else {
       STEP_TRY(mh_tc_backward_g(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
@@ -105,8 +129,11 @@ extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int 
     return MH_OK;
   }
   if (stash) {
-    STEP_TRY(mh_stash_prep(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
-                           ws->gty, stream));
+    if (fallback)
+      STEP_TRY(mh_tc_backward_g_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+                                     ws->label_local, state, lse2, ws->bc, nullptr, fallback, 1, stream));
+    STEP_TRY(mh_stash_prep_impl(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
+                                ws->gty, fallback, stream));
     xs = ws->xs;
     if (selfp) {
       if (dx) STEP_TRY(mh_tc_backward_dx(ws->bc, ws->B_pad, ws->C_pad, ws->w_hat, ws->dxhat_part, &n_split, ws->dx_sync, stream));

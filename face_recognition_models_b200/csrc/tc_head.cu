@@ -99,7 +99,15 @@ struct TcArgs {
   int raw_dw;                  // DW: write raw dw^ [C_pad, 512] instead of the projected dW
   int layout;                  // DW fused: parameter layout of dW
   int64_t ld;                  // DW fused: row pitch of dW
+  const int* gate;             // guarded stash (mh_step_*): the launch does nothing unless (*gate != 0) == (gate_on != 0); NULL: always runs
+  int gate_on;
 };
+
+// Guarded-stash fallback kernels are launched unconditionally and decide on the device (no host sync): every thread of
+// every CTA reads the same flag, which no kernel in flight writes, so the exit is uniform across the cluster.
+__device__ __forceinline__ bool gate_closed(const int* gate, int gate_on) {
+  return gate != nullptr && ((*reinterpret_cast<const volatile int*>(gate) != 0) != (gate_on != 0));
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -525,7 +533,7 @@ __device__ __forceinline__ void fwd_chunk_fix(const uint32_t (&v)[32], int col0,
                                               float hi, float ha, float hb, FwdAcc& acc, uint32_t (&pk)[16]) {
   const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid) || (STASH && !rc.valid);
   if (!slow) {
-    float l2[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
+    float l2[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f}, z2[2] = {0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 32; k += 2) {
       float es[2];
@@ -537,12 +545,14 @@ __device__ __forceinline__ void fwd_chunk_fix(const uint32_t (&v)[32], int col0,
         c2[h] += __saturatef(fmaf(c, CNT_BIG, rc.ntbig));
         const float e = ex2(fmaf(u, rc.scale2, rc.nref2));
         l2[h] += e;
+        if (V == V_SPHERE) z2[h] = fmaf(e, u, z2[h]);
         es[h] = STASH ? e * elem_du<V>(raw, c, rc.thr, ha) : e;
       }
       if (STASH) pk[k >> 1] = pack_bf16(es[0], es[1]);
     }
     acc.l += l2[0] + l2[1];
     acc.cntf += c2[0] + c2[1];
+    if (V == V_SPHERE) acc.ez += z2[0] + z2[1];
   } else {
 #pragma unroll
     for (int k = 0; k < 32; k += 2) {
@@ -555,11 +565,13 @@ __device__ __forceinline__ void fwd_chunk_fix(const uint32_t (&v)[32], int col0,
         const int col = col0 + k + h;
         float e = ex2(fmaf(u, rc.scale2, rc.nref2));
         float sv = e * elem_du<V>(raw, c, rc.thr, ha);
-        if (col == rc.tcol) { e = ex2(rc.zt2 + rc.nref2); sv = 0.f; }
+        float ue = u;
+        if (col == rc.tcol) { e = ex2(rc.zt2 + rc.nref2); sv = 0.f; ue = (rc.scale2 != 0.f) ? rc.zt2 / rc.scale2 : 0.f; }
         else if (col < nvalid && c > rc.t) acc.cnt += 1;
         if (col >= nvalid) { e = 0.f; sv = 0.f; }
         if (!rc.valid) sv = 0.f;
         acc.l += e;
+        if (V == V_SPHERE) acc.ez = fmaf(e, ue, acc.ez);
         es[h] = sv;
       }
       if (STASH) pk[k >> 1] = pack_bf16(es[0], es[1]);
@@ -969,7 +981,7 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
             else fwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc);
           } else {
             if (MODE == MODE_FWDS) {
-              fwd_chunk_fix<V == V_SPHERE ? V_CLAMP : V, true>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc, pk);
+              fwd_chunk_fix<V, true>(cur, col0, nvalid, rc, lo, hi, ha, hb, acc, pk);
             } else {
               float qv[32];
               bwd_chunk<V>(cur, col0, nvalid, rc, lo, hi, ha, hb, pk, qv);
@@ -1198,6 +1210,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
+  if (gate_closed(a.gate, a.gate_on)) return;
   tc_body<MODE, V>(tmA, tmB, a, blockIdx.x >> 1, gridDim.x >> 1, smem_raw);   // tile-scheduling unit: CTA pair
 }
 
@@ -1435,18 +1448,12 @@ int variant_of(const MhParams& p) {
 
 template <int MODE>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cudaStream_t st) {
-  const int v = variant_of(args.p);
-  if (MODE == MODE_FWDS && v != V_PLAIN && v != V_CLAMP && v != V_MV) {
-    mh_set_error("the forward stash is not built for this family (see mh_tc_stash_ok)");
-    return MH_ERR_ARG;
-  }
-  constexpr int M2 = MODE == MODE_FWDS ? MODE_FWD : MODE;       // never instantiated for FWDS (guarded above)
-  switch (v) {
+  switch (variant_of(args.p)) {
     case V_PLAIN: return launch<MODE, V_PLAIN>(ta, tb, args, st);
     case V_CLAMP: return launch<MODE, V_CLAMP>(ta, tb, args, st);
-    case V_SPHERE: return launch<M2, V_SPHERE>(ta, tb, args, st);
+    case V_SPHERE: return launch<MODE, V_SPHERE>(ta, tb, args, st);
     case V_MV: return launch<MODE, V_MV>(ta, tb, args, st);
-    default: return launch<M2, V_CURR>(ta, tb, args, st);
+    default: return launch<MODE, V_CURR>(ta, tb, args, st);
   }
 }
 
@@ -1474,7 +1481,8 @@ int check_common(int64_t B, int64_t B_pad, int64_t C, int64_t C_pad) {
 extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { (void)C_pad; return 2 * (int64_t)(num_sms() / 2); }
 
 // records of rows a pair never visits stay at the merge identity (max = -inf, sums = 0)
-__global__ void stats_identity_kernel(float* __restrict__ st, int64_t n_parts, int64_t B_pad) {
+__global__ void stats_identity_kernel(float* __restrict__ st, int64_t n_parts, int64_t B_pad, const int* gate, int gate_on) {
+  if (gate_closed(gate, gate_on)) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = n_parts * MH_ST_PLANES * B_pad;
   if (i < n) st[i] = ((i / B_pad) % MH_ST_PLANES == MH_ST_M) ? -INFINITY : 0.f;
@@ -1497,6 +1505,20 @@ extern "C" int mh_tc_stash_ok(const mh_config* cfg_host, int64_t C) {
   if (!mh_tc_fixref_ok(cfg_host, C)) return 0;
   const MhParams p = mh_make_params(cfg_host);
   return (p.hard_kind == 0 || (p.hard_kind == 1 && p.hard_a > 1.f)) ? 1 : 0;
+}
+
+// Guarded stash: heads that fail the proof above (CurricularFace at s = 64: 277 binades; SphereFace: the scale is |x_i|;
+// any family at s > 69) may still stash against the fixed reference ref_i = scale_i log2e umax - 102.  Nothing can
+// overflow (u <= umax), but terms below 2^-126 flush to zero; that is harmless exactly when the row's sum is large
+// against everything that can have been flushed, sum_j e_ij >= C 2^-102 (flushed mass <= C 2^-126: < 2^-24 relative, in
+// the loss and in every gradient entry).  mh_finalize_rows_guarded checks this per row on the device; a batch with an
+// unsafe row re-runs the general path (online-max forward, recomputed G) through launches gated on that flag.  Rows
+// fail only when EVERY class logit sits > 100 nats below scale*umax, e.g. a handful of classes all anti-aligned with x.
+extern "C" int mh_tc_stash_guarded_ok(const mh_config* cfg_host, int64_t C) {
+  if (!cfg_host || C < 2) return 0;
+  const MhParams p = mh_make_params(cfg_host);
+  if (!p.scale_is_norm && !(p.s > 0.f)) return 0;
+  return mh_tc_stash_ok(cfg_host, C) ? 0 : 1;
 }
 
 // Test hook (host only, no device work): the (pair, m_tile, n_tile) triples of the A-stationary schedule in
@@ -1524,14 +1546,14 @@ template <int MODE>
 static int launch_s_tiles(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
                           int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
                           const float* state, const float* lse2, float* stats_tiles, void* bc_bf16, float* r_colsum,
-                          cudaStream_t st) {
+                          cudaStream_t st, const int* gate = nullptr, int gate_on = 0) {
   const int units = num_sms() / 2;
   CUtensorMap tb;
   if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN / 2)) return e;
   const int64_t rows_per_launch = (int64_t)units * BMT;
   if (stats_tiles) {
     const int64_t n = 2 * (int64_t)units * MH_ST_PLANES * B_pad;
-    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * units, B_pad);
+    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * units, B_pad, gate, gate_on);
   }
   for (int64_t r0 = 0; r0 < B_pad; r0 += rows_per_launch) {
     const int64_t rows = std::min(rows_per_launch, B_pad - r0);
@@ -1552,37 +1574,60 @@ static int launch_s_tiles(const mh_config* cfg_host, const void* x_hat_bf16, int
     a.stats_tiles = stats_tiles ? stats_tiles + r0 : nullptr;
     a.G = bc_bf16 ? (__nv_bfloat16*)bc_bf16 + r0 * 128 : nullptr;
     a.rsum = r_colsum;
+    a.gate = gate; a.gate_on = gate_on;
     if (int e = launch_variant<MODE>(ta, tb, a, st)) return e;
   }
   return MH_OK;
+}
+
+// stash_kind: 0 no stash, 1 the proven stash (mh_tc_stash_ok), 2 the guarded stash (mh_tc_stash_guarded_ok: the caller
+// checks the row sums afterwards, see mh_step_forward).  gate: see TcArgs::gate.
+int mh_tc_forward_impl(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
+                       int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
+                       const float* state, float* stats_tiles, void* stash_bf16, int stash_kind, const int* gate,
+                       int gate_on, void* stream) {
+  MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && stats_tiles, "null pointer");
+  if (int e = check_common(B, B_pad, C, C_pad)) return e;
+  MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
+  if (stash_bf16) {
+    if (stash_kind == 2)
+      MH_CHECK_ARG(mh_tc_stash_guarded_ok(cfg_host, C), "head not eligible for the guarded stash (see mh_tc_stash_guarded_ok)");
+    else
+      MH_CHECK_ARG(mh_tc_stash_ok(cfg_host, C), "head not eligible for the forward stash (see mh_tc_stash_ok)");
+    return launch_s_tiles<MODE_FWDS>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+                                     nullptr, stats_tiles, stash_bf16, nullptr, (cudaStream_t)stream, gate, gate_on);
+  }
+  return launch_s_tiles<MODE_FWD>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+                                  nullptr, stats_tiles, nullptr, nullptr, (cudaStream_t)stream, gate, gate_on);
 }
 
 extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                              const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                              const int32_t* label_local, const float* state, float* stats_tiles, void* stash_bf16,
                              void* stream) {
-  MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && stats_tiles, "null pointer");
+  return mh_tc_forward_impl(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+                            stats_tiles, stash_bf16, 1, nullptr, 0, stream);
+}
+
+int mh_tc_backward_g_impl(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
+                          const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
+                          const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
+                          float* r_colsum, const int* gate, int gate_on, void* stream) {
+  MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && lse2 && G_bf16, "null pointer");
   if (int e = check_common(B, B_pad, C, C_pad)) return e;
   MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
-  if (stash_bf16) {
-    MH_CHECK_ARG(mh_tc_stash_ok(cfg_host, C), "head not eligible for the forward stash (see mh_tc_stash_ok)");
-    return launch_s_tiles<MODE_FWDS>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
-                                     nullptr, stats_tiles, stash_bf16, nullptr, (cudaStream_t)stream);
-  }
-  return launch_s_tiles<MODE_FWD>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
-                                  nullptr, stats_tiles, nullptr, nullptr, (cudaStream_t)stream);
+  MH_CHECK_ARG(!(gate && r_colsum), "a gated backward-G launch takes no column sums");
+  if (r_colsum) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
+  return launch_s_tiles<MODE_BWD_G>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+                                    lse2, nullptr, G_bf16, r_colsum, (cudaStream_t)stream, gate, gate_on);
 }
 
 extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                                 const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                                 const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
                                 float* r_colsum, void* stream) {
-  MH_CHECK_ARG(cfg_host && x_hat_bf16 && w_hat_bf16 && rowp && label_local && state && lse2 && G_bf16, "null pointer");
-  if (int e = check_common(B, B_pad, C, C_pad)) return e;
-  MH_CHECK_ARG(ldp >= B_pad, "rowp pitch must cover B_pad");
-  if (r_colsum) MH_CUDA_OK(cudaMemsetAsync(r_colsum, 0, sizeof(float) * C_pad, (cudaStream_t)stream));
-  return launch_s_tiles<MODE_BWD_G>(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
-                                    lse2, nullptr, G_bf16, r_colsum, (cudaStream_t)stream);
+  return mh_tc_backward_g_impl(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state, lse2,
+                               G_bf16, r_colsum, nullptr, 0, stream);
 }
 
 // side pass of the stash backward (NULL rho = plain dx GEMM)
@@ -1889,7 +1934,7 @@ extern "C" int mh_tc_forward_pw(const mh_config* cfg_host, const void* x_hat_bf1
   MH_CUDA_OK(cudaMemsetAsync(ready_ws, 0, sizeof(int) * (size_t)(n_ct + 1), st));
   {
     const int64_t n = 2 * (int64_t)pairs * MH_ST_PLANES * B_pad;
-    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * pairs, B_pad);
+    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * pairs, B_pad, nullptr, 0);
   }
   CUtensorMap ta, tb;
   if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN / 2)) return e;

@@ -85,6 +85,7 @@ def _round_up(a: int, b: int) -> int:
 
 
 _DT = {torch.float32: L.DT_F32, torch.bfloat16: L.DT_BF16, torch.float16: L.DT_F16}
+GUARDED_MIN_BC = 1 << 25        # smallest B_pad * C_pad at which backward_mode = 'auto' takes the guarded stash
 _DEVICE_OK = set()
 
 
@@ -139,9 +140,9 @@ class HeadEngine:
         if self.mode != "tc" or self.backward_mode == "recompute":
             return False
         ok = bool(L.load().mh_tc_stash_ok(C.byref(self.cfg), self.C))
-        if self.backward_mode == "stash" and not ok:
+        if self.backward_mode == "stash" and not ok and not L.load().mh_tc_stash_guarded_ok(C.byref(self.cfg), self.C):
             raise L.MarginHeadError("backward_mode='stash' needs a head that passes mh_tc_stash_ok (fixed scale with "
-                                    "s*log2(e)*2 <= 200, no hard-negative re-weighting)")
+                                    "s*log2(e)*2 <= 200, no hard-negative re-weighting) or mh_tc_stash_guarded_ok")
         return ok
 
     # -- workspace ------------------------------------------------------------------------------
@@ -163,8 +164,22 @@ class HeadEngine:
         key = (self.backward_mode, self.mode, self.family, float(self.cfg.s), float(self.cfg.mv_weight), self.C)
         if self._stash_ok_key != key:
             self._stash_ok_val = self.stash_ok()
+            self._stash_guard_val = bool(self.mode == "tc" and self.backward_mode != "recompute" and not self._stash_ok_val
+                                         and L.load().mh_tc_stash_guarded_ok(C.byref(self.cfg), self.C))
             self._stash_ok_key = key
         return self._stash_ok_val
+
+    def _stash_kind(self, B_pad: int, C_pad: int) -> int:
+        """0 recompute, 1 the proven stash (mh_tc_stash_ok), 2 the guarded stash of the step API (CurricularFace, SphereFace,
+        s > 69: fixed-reference forward + stash run speculatively, a device-side check of the row sums decides whether the
+        general path has to re-run; mh_tc_stash_guarded_ok).  'auto' takes the guarded stash where a whole GEMM pass costs more
+        than its handful of gated launches (B_pad * C_pad >= 2^25); backward_mode = 'stash' takes it at any size."""
+        if self._stash_ok_cached():
+            return 1
+        if self._stash_guard_val and os.environ.get("MH_STASH_GUARDED", "1") != "0":
+            if self.backward_mode == "stash" or B_pad * C_pad >= GUARDED_MIN_BC:
+                return 2
+        return 0
 
     def invalidate_shadow(self):
         """Forget the w_hat left by sgd_step().  Only needed after writing the parameter behind autograd's back
@@ -374,7 +389,8 @@ class HeadEngine:
         launch-bound configs).  The descriptor is rebuilt only when a shape, dtype or workspace pointer changes."""
         dev = x.device
         Cn = self.C
-        stash = bool(want_grad and self._stash_ok_cached())
+        stash = self._stash_kind(B_pad, C_pad) if want_grad else 0        # 0 none / recompute, 1 stash, 2 guarded stash
+        guarded = stash == 2
         key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj(), _merged_bwd(), _merged_fwd())
         if self._step_key != key:
             lib = L.load()
@@ -390,7 +406,7 @@ class HeadEngine:
                 merge_scratch=b("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev),
                 stats=b("stats", (L.ST_PLANES, B_pad), torch.float32, dev),
                 rowout=b("rowout", (L.RO_PLANES, B_pad), torch.float32, dev))
-            if _merged_fwd() and self.layout == L.LAYOUT_CD:
+            if _merged_fwd() and self.layout == L.LAYOUT_CD and not guarded:
                 T.update(pw_ready=b("pw_ready", (C_pad // L.NTILE + 1,), torch.int32, dev))
             part_splits = 0
             if want_grad:
@@ -400,10 +416,12 @@ class HeadEngine:
                 T.update(bc=b("G", (B_pad, C_pad), torch.bfloat16, dev),
                          dxhat_part=b("dxhat_part", (part_splits, B_pad, L.D), torch.float32, dev),
                          gscal=b("gscal", (2,), torch.float32, dev), dx_sync=b("dx_sync", (L.DX_SYNC_INTS,), torch.int32, dev))
-                if _selfproj() or _merged_bwd():
+                if _selfproj() or _merged_bwd() or guarded:
                     T.update(rpart=b("dw_rpart", (4, C_pad), torch.float32, dev),
                              rflag=b("dw_rflag", (C_pad // L.TILE,), torch.int32, dev))
-                if not _selfproj():
+                if guarded:      # the guarded stash always projects inside the dW kernel (its stash does not give cos back)
+                    T.update(guard=b("stash_guard", (1,), torch.int32, dev, zero=True))
+                elif not _selfproj():
                     T.update(r_colsum=b("r_colsum", (B_pad // L.TILE if stash else 1, C_pad), torch.float32, dev))
                 if _merged_bwd():
                     T.update(prog=b("bwd_prog", (2,), torch.int32, dev))
@@ -434,7 +452,7 @@ class HeadEngine:
             margins = None
         scalars = torch.empty(4, dtype=torch.float32, device=dev)      # loss, acc@1, acc@5, loss_g (fresh: returned to the user)
         L.call("mh_step_forward", C.byref(self.cfg), C.byref(ws), _ptr(x), _ptr(labels), _ptr(W), _ptr(margins), _ptr(state),
-               1 if update_state else 0, 1 if run_pw else 0, 1 if stash else 0, _ptr(scalars), _stream())
+               1 if update_state else 0, 1 if run_pw else 0, stash, _ptr(scalars), _stream())
         return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=T["w_hat"], w_hat32=None, inv_norm=T["inv_norm"],
                     x_hat=T["x_hat"], x_hat32=T["x_hat32"], xnorm=T["xnorm"], label_local=T["label_local"], rowp=T["rowp"],
                     rowout=T["rowout"], scalars=scalars, S=None, pre=None, logits=None, exact=False, gen=self._gen,
@@ -460,7 +478,7 @@ class HeadEngine:
                 g_lossg = g_lossg.float()
             dx = torch.empty((B, L.D), dtype=ctx["x_dtype"], device=dev) if need_dx else None
             dW = torch.empty(ctx["W_shape"], dtype=torch.float32, device=dev) if need_dw else None
-            L.call("mh_step_backward", C.byref(self.cfg), C.byref(ctx["step_ws"]), 1 if ctx["step_stash"] else 0,
+            L.call("mh_step_backward", C.byref(self.cfg), C.byref(ctx["step_ws"]), int(ctx["step_stash"]),
                    _ptr(ctx["state"]), _ptr(g_loss), _ptr(g_lossg), _ptr(dx), _ptr(dW), st)
             return dx, dW
         gscal = self._gscal(g_loss, g_lossg, B, dev)

@@ -176,6 +176,11 @@ int mh_tc_fixref_ok(const mh_config* cfg_host, int64_t C);
 /* 1 when the forward may stash for the backward: mh_tc_fixref_ok and cos_ij recoverable from the stashed exponential
  * (u = cos, or MV-Softmax's invertible u = w*cos + w - 1; not CurricularFace's cos*(t + cos)).  Otherwise: recompute. */
 int mh_tc_stash_ok(const mh_config* cfg_host, int64_t C);
+/* 1 when the head fails mh_tc_stash_ok but may use the GUARDED stash of mh_step_forward (stash == 2): CurricularFace
+ * (criterion.py:491-587; s*log2e*3 = 277 binades at s = 64), SphereFace (criterion.py:12-107; the scale is |x_i|) and
+ * any family whose s is too large for the proof.  The fixed reference ref_i = scale_i*log2e*umax - 102 still rules out
+ * overflow; whether terms flushed to zero could matter is checked per row on the device after the forward. */
+int mh_tc_stash_guarded_ok(const mh_config* cfg_host, int64_t C);
 
 /* Fused cos-GEMM + margin + softmax statistics (replaces F.linear/torch.mm at criterion.py:65,176,267,
  * 408,545,868,990,1100,1256, the elementwise margin passes and nn.CrossEntropyLoss's log-softmax,
@@ -387,11 +392,18 @@ typedef struct mh_step_ws {
                                   (mh_tc_forward_pw) whenever the W prologue has to run and the head / shape is eligible */
   int32_t* prog;               /* [2] or NULL; non-NULL (with rpart / rflag) selects the merged dx + dW kernel
                                   (mh_tc_backward_dxdw) whenever both gradients are wanted and the shape is eligible */
+  int32_t* guard;              /* [1] or NULL; needed by the guarded stash (stash == 2): 1 after a forward whose fixed-reference
+                                  sums could not be trusted and that therefore re-ran the general path on the device */
 } mh_step_ws;
 
 /* Forward of one step: mh_prologue_w (skipped when run_prologue_w == 0: w_hat / inv_norm already hold this W, e.g.
- * after mh_sgd_step_w), mh_prologue_x, mh_row_params, mh_tc_forward (stashing into ws->bc when stash != 0; needs
- * mh_tc_stash_ok), mh_merge_stats, mh_finalize_rows.  scalars[4] = {mean CE loss, acc@1 %, acc@5 %, loss_g}.
+ * after mh_sgd_step_w), mh_prologue_x, mh_row_params, mh_tc_forward (stashing into ws->bc when stash != 0; stash == 1
+ * needs mh_tc_stash_ok), mh_merge_stats, mh_finalize_rows.  scalars[4] = {mean CE loss, acc@1 %, acc@5 %, loss_g}.
+ * stash == 2, the GUARDED stash (needs mh_tc_stash_guarded_ok and ws->guard; CurricularFace criterion.py:491-587,
+ * SphereFace criterion.py:12-107, any family at s > 69): the fixed-reference forward + stash runs speculatively, the
+ * finaliser checks on the device that no row's sum can have lost anything to underflow (row sum >= C 2^-102) and
+ * writes ws->guard; the general online-max forward, its merge and its finaliser are enqueued behind it as launches
+ * that return at once unless the flag is set.  No host synchronisation, same results as the general path to 2^-24.
  * Replaces the head forward + nn.CrossEntropyLoss + accuracy of model_utils.py:177-182 in ONE host call. */
 int mh_step_forward(const mh_config* cfg_host, const mh_step_ws* ws, const void* x, const int64_t* labels,
                     const float* W, const float* margins, float* state, int update_state, int run_prologue_w,
@@ -403,6 +415,9 @@ int mh_step_forward(const mh_config* cfg_host, const mh_step_ws* ws, const void*
  * mh_norm_backward_x, mh_tc_backward_dw_fused); with ws->r_colsum == NULL the dW kernel is mh_tc_backward_dw_proj
  * and the dx GEMM runs without its side pass.  g_loss / g_lossg: device scalars (upstream gradients of loss / loss_g; NULL = 0).
  * dx ([B, 512] in x_dtype) and dW (parameter layout, fp32) may each be NULL to skip that gradient.
+ * stash == 2 (guarded stash): the stash backward with the self-projecting dW kernel (ws->r_colsum must be NULL); a
+ * gated mh_tc_backward_g first rewrites ws->bc with the recomputed G when the forward raised ws->guard, and
+ * mh_stash_prep then uses rho = 1 and no separate target-column term.
  * Replaces autograd's backward of model_utils.py:185 through the head in ONE host call. */
 int mh_step_backward(const mh_config* cfg_host, const mh_step_ws* ws, int stash, const float* state,
                      const float* g_loss, const float* g_lossg, void* dx, float* dW, void* stream);

@@ -44,6 +44,49 @@ def test_config_struct_layout():
     assert _lib.MhConfig.s.offset == 16 and _lib.MhConfig.sphere_lambda.offset == 56
 
 
+def test_step_workspace_struct_mirrors_the_header():
+    """MhStepWs (ctypes) must list the fields of mh_step_ws in the header's order and widths (all 8 bytes except the two
+    int32 enums): the descriptor crosses the FFI by pointer."""
+    from face_recognition_models_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "margin_head.h")).read()
+    body = re.search(r"typedef struct mh_step_ws \{(.*?)\} mh_step_ws;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.rsplit(" ", 1)[0], decl.split(",")
+        first = names[0].rsplit(" ", 1)
+        base = first[0].strip()
+        for n in [first[1]] + names[1:]:
+            fields.append((n.strip().lstrip("*"), 4 if base == "int32_t" and "*" not in n and not base.endswith("*") else 8))
+    assert [f[0] for f in fields] == [f[0] for f in _lib.MhStepWs._fields_]
+    assert [f[1] for f in fields] == [ctypes.sizeof(f[1]) for f in _lib.MhStepWs._fields_]
+    assert fields[-1][0] == "guard"
+
+
+def test_stash_eligibility_predicates(lib):
+    """Host-only: the proven stash (mh_tc_stash_ok) and the guarded stash (mh_tc_stash_guarded_ok) partition the heads."""
+    from face_recognition_models_b200 import _lib
+    def cfg(fam, s=64.0, **kw):
+        c = _lib.MhConfig()
+        c.family = _lib.FAMILY[fam]
+        c.s = s
+        c.m = 0.5
+        c.mv_weight = 1.12
+        c.sphere_m = 2
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+    for fam, s, proven in [("arcface", 64.0, 1), ("cosface", 64.0, 1), ("mv_am", 32.0, 1), ("curricularface", 64.0, 0),
+                           ("sphereface", 64.0, 0), ("arcface", 128.0, 0)]:
+        c = cfg(fam, s)
+        assert lib.mh_tc_stash_ok(ctypes.byref(c), 1000) == proven, fam
+        assert lib.mh_tc_stash_guarded_ok(ctypes.byref(c), 1000) == 1 - proven, fam
+        assert lib.mh_tc_stash_guarded_ok(ctypes.byref(c), 1) == 0
+
+
 def test_version_and_error_strings(lib):
     assert b"sm_100a" in lib.mh_version()
     assert isinstance(lib.mh_last_error(), bytes)

@@ -514,6 +514,7 @@ def run_b200(args):
     peaks = load_peaks()
     small = 6.0 * Cn * D < 2.5 * (126 << 20)              # fp32 W + bf16 w^ fit in (or near) the 126 MB L2: flush between steps
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev) if small else None
+    flush_sink = torch.zeros((), dtype=torch.float32, device=dev)
 
     def barrier():
         if world > 1:
@@ -537,6 +538,8 @@ def run_b200(args):
             evs = []
             for _ in range(steps):
                 flush.zero_()
+                if args.flush == "clean":
+                    flush_sink.copy_(flush.sum())      # read pass: the dirty lines of the write are written back HERE, not inside the step
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 fn()
@@ -587,9 +590,19 @@ def run_b200(args):
             out.loss.backward()
             return out
 
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = torch.cuda.Event()
+
         def step_e2e():
-            x_dev.copy_(x_host, non_blocking=True)
-            y_dev.copy_(y_host, non_blocking=True)
+            # the W prologue does not depend on the batch: enqueue it first (head.prefetch()), and bring the batch in on a
+            # copy stream beside it -- what a training loop with a prefetching data loader does; the step waits for the copy
+            if world == 1:
+                head.prefetch()
+            with torch.cuda.stream(copy_stream):
+                x_dev.copy_(x_host, non_blocking=True)
+                y_dev.copy_(y_host, non_blocking=True)
+                copied.record()
+            torch.cuda.current_stream().wait_event(copied)
             xg = x_dev.detach().requires_grad_(True)
             W.grad = None
             out = head.fused_loss(xg, y_dev)
@@ -600,18 +613,26 @@ def run_b200(args):
             torch.cuda.current_stream().synchronize()        # the caller reads loss/acc every step (model_utils.py:190)
             return float(res_host[0])
 
-        for _ in range(max(args.warmup, 3)):
-            out = step_resident()
+        def arm(fn, steps):
+            """One timed arm: idle gap, W warm-up steps, K timed steps.  Every arm (device-resident, end-to-end, the other
+            backward mode) starts from the same power / thermal state: the part is power-capped, its clock under load
+            settles within a few hundred milliseconds, and an arm that simply ran after another one would be measured
+            in a different regime (the resident arm in the boost, the next one throttled)."""
+            torch.cuda.synchronize()
+            time.sleep(args.idle_s)
+            for _ in range(max(args.warmup, 3)):
+                fn()
+            return timed(fn, steps)
+
+        out = step_resident()
         torch.cuda.synchronize()
         loss_val = float(out.loss.detach())
         if sampler:
             sampler.active = True
         # ---- device-resident arm -----------------------------------------------------------------------------------
-        ms = timed(step_resident, args.steps)
-        # ---- end-to-end arm (host buffers), right after the device-resident arm: both see the same power state --------
-        for _ in range(2):
-            step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
+        ms = arm(step_resident, args.steps)
+        # ---- end-to-end arm (host buffers): same protocol -------------------------------------------------------------
+        ms_e2e = arm(step_e2e, args.steps)
         # ---- the same K steps again with CUDA events around every C-ABI entry point on the launching stream (the
         # product path issues a step as two calls, mh_step_forward / mh_step_backward; MH_STEP_API=0 drives the same
         # kernels one entry point at a time so that each can be timed): feeds `kernels` and `roofline`, not `value`
@@ -630,12 +651,13 @@ def run_b200(args):
             step_resident()
         # ---- the other backward mode (recompute: north_star's "backward recomputes logit tiles"), same protocol ----
         ms_alt = None
-        stash = eng.stash_ok()
+        # 0 recompute, 1 the proven stash, 2 the guarded stash (step API, single GPU; CurricularFace / SphereFace at scale)
+        stash = 1 if eng.stash_ok() else 0
+        if not stash and world == 1:
+            stash = eng._stash_kind((B + 255) // 256 * 256, (eng.C + 255) // 256 * 256)
         if stash:
             eng.backward_mode = "recompute"
-            for _ in range(3):
-                step_resident()
-            ms_alt = timed(step_resident, args.steps)
+            ms_alt = arm(step_resident, args.steps)
             eng.backward_mode = "auto"
             for _ in range(2):
                 step_resident()
@@ -654,10 +676,11 @@ def run_b200(args):
         tot_ms += ms
         tot_ms_e2e += ms_e2e
         tot_ms_alt += ms_alt or 0.0
-        backward_desc = ("stash (forward writes a bf16 B x C stash; 3 GEMM passes per step)" if stash
-                         else "recompute (4 GEMM passes per step)")
+        backward_desc = ("stash (forward writes a bf16 B x C stash; 3 GEMM passes per step)" if stash == 1 else
+                         "guarded stash (speculative fixed-reference stash checked on the device; 3 GEMM passes per step)"
+                         if stash == 2 else "recompute (4 GEMM passes per step)")
         fam_res[fam] = {"ms_per_step": round(ms / args.steps, 4), "e2e_ms_per_step": round(ms_e2e / args.steps, 4),
-                        "backward": "stash" if stash else "recompute", "loss": loss_val,
+                        "backward": ("recompute", "stash", "guarded stash")[stash], "loss": loss_val,
                         **({"recompute_ms_per_step": round(ms_alt / args.steps, 4)} if ms_alt else {})}
         W_rows = W.shape[0] if eng.layout == L.LAYOUT_CD else W.shape[1]
         del head, W, eng, x, y, x_dev, y_dev
@@ -750,7 +773,8 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["workload"], "B_per_gpu": B, "C": Cn, "d": D, "parallelism": f"class-shard x{world}",
                        "families": fam_res, "backward": backward_desc,
-                       "l2": (f"flushed between steps (256 MB write outside each step's CUDA-event pair; fp32 W + bf16 w^ = "
+                       "l2": (f"flushed between steps (256 MB write{' + 256 MB read, so that the step does not pay the write-back of the flush buffer' if args.flush == 'clean' else ''}"
+                              f" outside each step's CUDA-event pair; fp32 W + bf16 w^ = "
                               f"{6.0 * Cn * D / 2 ** 20:.0f} MB vs 126 MB L2); per-step times summed") if small else
                              "inputs_exceed_l2 (W fp32 4.1 GB + bf16 2 GB per step vs 126 MB L2)",
                        "loss": loss_val},
@@ -891,6 +915,12 @@ def main():
     ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
     ap.add_argument("--C", type=int, default=0, help="override the config's class count")
     ap.add_argument("--B", type=int, default=0, help="override the config's per-GPU batch")
+    ap.add_argument("--flush", default="clean", choices=["clean", "write"],
+                    help="small configs (cfg2/cfg3), L2 flush before every step: 'write' = a 256 MB write; 'clean' = the write "
+                         "followed by a 256 MB read, so that the first kernels of the step do not pay the write-back of the "
+                         "flush buffer's dirty lines")
+    ap.add_argument("--idle-s", type=float, default=1.0, dest="idle_s",
+                    help="idle gap before the warm-up of every timed arm (same power / thermal starting state for each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 parity self-check (outside the timed region)")
     ap.add_argument("--no-gpu-context", action="store_true", help="skip the stock-PyTorch / cuBLAS context block")

@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, version, device check, hyper-parameter expansion.
 #include "common.cuh"
+#include <stdlib.h>
 #include <cstdarg>
 #include <cstdio>
 
@@ -80,6 +81,13 @@ MhParams mh_make_params(const mh_config* c) {
     default: p.lo = (float)(-1 + 1e-7); p.hi = (float)(1 - 1e-7); break;              // criterion.py:994,1104,1260
   }
   return p;
+}
+
+bool mh_pdl_enabled() {
+  // off by default: measured on B200 it costs BASELINE config 3 0.53 -> 0.61 ms per step and changes nothing at configs 2
+  // and 4 (profiles/r2_ab_pdl_flush.txt); MH_PDL=1 turns it on
+  static const bool on = [] { const char* e = getenv("MH_PDL"); return e && e[0] == '1'; }();
+  return on;
 }
 
 float mh_family_umax(const MhParams* p) {

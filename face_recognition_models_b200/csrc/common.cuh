@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <mutex>
+#include <utility>
 #include "../../include/margin_head.h"
 
 #define MH_LOG2E 1.4426950408889634f
@@ -58,6 +59,39 @@ inline cudaError_t mh_once_per_device(MhDeviceOnce& o, Fn&& fn) {
 }
 // SM count of the CURRENT device (cached per device ordinal; 148 if the query fails).
 int mh_num_sms();
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// A step is a chain of ~15 dependent launches, most of them O(B*d) kernels of a few microseconds; BASELINE configs 2 and 3
+// are bounded by that chain.  Every kernel of this library is launched with the programmatic-stream-serialization
+// attribute and starts with mh_pdl_sync(): `griddepcontrol.wait` (all prerequisite grids complete, their writes visible)
+// followed by `griddepcontrol.launch_dependents` (the next kernel of the stream may be scheduled now; it parks in its own
+// wait).  Launch latency and CTA ramp-up of kernel N+1 thus overlap the body of kernel N, while the data dependencies
+// stay exactly those of plain stream order: nothing is read or written before the wait, and a kernel only triggers
+// after its own wait, so completion is transitive along the chain.  Kernels of other libraries (torch, NCCL) in between
+// never trigger early, so the attribute degrades to ordinary serialization next to them.  OPT-IN (MH_PDL=1): measured,
+// it does not pay on this part -- config 3 gets slower, configs 2 and 4 do not move -- so by
+// default no launch carries the attribute and the two instructions at the top of every kernel are no-ops.
+bool mh_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void mh_pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... Params, typename... Args>
+inline cudaError_t mh_launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mh_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(std::forward<Args>(args))...);
+}
+#endif
 
 // Device copy of the hyper-parameters + derived constants, passed by value to kernels.
 struct MhParams {

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(int64_t M, int64_t N
                                                             int64_t a_rs, int64_t a_cs, const float* __restrict__ Bm,
                                                             int64_t b_rs, int64_t b_cs, float* __restrict__ Cm,
                                                             int64_t ldc) {
+  mh_pdl_sync();
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Bs[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
@@ -75,7 +76,7 @@ extern "C" int mh_sgemm_strided(int64_t M, int64_t N, int64_t K, const float* A,
   MH_CHECK_ARG(M > 0 && N > 0 && K > 0 && ldc >= N, "bad shape");
   dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
   MH_CHECK_ARG(grid.y <= 65535, "M too large for the exact path");
-  sgemm_strided_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc);
+  mh_launch(sgemm_strided_kernel, grid, 256, 0, (cudaStream_t)stream, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc);
   MH_LAUNCH_OK();
   return MH_OK;
 }
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) dense_forward_kernel(MhParams p, const fl
                                                             const int32_t* __restrict__ label_local,
                                                             const float* __restrict__ state, float* __restrict__ stats,
                                                             float* __restrict__ pre, float* __restrict__ logits) {
+  mh_pdl_sync();
   __shared__ RowStat sh[8];
   const int64_t i = blockIdx.x;
   const float scale = rowp[MH_RP_SCALE * ldp + i], thr = rowp[MH_RP_THR * ldp + i];
@@ -152,7 +154,7 @@ extern "C" int mh_dense_forward(const mh_config* cfg_host, const float* S, int64
   MH_CHECK_ARG(cfg_host && S && rowp && label_local && state && stats, "null pointer");
   MH_CHECK_ARG(B > 0 && C > 0 && lds_ >= C && B_pad >= B, "bad shape");
   MhParams p = mh_make_params(cfg_host);
-  dense_forward_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(p, S, lds_, B, B_pad, C, rowp, ldp, label_local,
+  mh_launch(dense_forward_kernel, (unsigned)B, 256, 0, (cudaStream_t)stream, p, S, lds_, B, B_pad, C, rowp, ldp, label_local,
                                                                     state, stats, pre, logits);
   MH_LAUNCH_OK();
   return MH_OK;
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(256) dense_backward_dc_kernel(MhParams p, floa
                                                                 const float* __restrict__ lse2,
                                                                 const float* __restrict__ dlogits,
                                                                 const float* __restrict__ dpre, float* __restrict__ rowaux) {
+  mh_pdl_sync();
   __shared__ float red[8];
   const int64_t i = blockIdx.x;
   const float scale = rowp[MH_RP_SCALE * ldp + i], thr = rowp[MH_RP_THR * ldp + i];
@@ -220,7 +223,7 @@ extern "C" int mh_dense_backward_dc(const mh_config* cfg_host, float* S, int64_t
   MH_CHECK_ARG((lse2 != nullptr) != (dlogits != nullptr), "exactly one of lse2 / dlogits must be given");
   MH_CHECK_ARG(!dlogits || rowaux, "compat mode needs rowaux");
   MhParams p = mh_make_params(cfg_host);
-  dense_backward_dc_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(p, S, lds_, B, C, rowp, ldp, label_local,
+  mh_launch(dense_backward_dc_kernel, (unsigned)B, 256, 0, (cudaStream_t)stream, p, S, lds_, B, C, rowp, ldp, label_local,
                                                                         state, lse2, dlogits, dpre, rowaux);
   MH_LAUNCH_OK();
   return MH_OK;
@@ -231,6 +234,7 @@ extern "C" int mh_dense_backward_dc(const mh_config* cfg_host, float* S, int64_t
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) merge_stats_kernel(const float* __restrict__ in, int64_t n_parts, int64_t lds_,
                                                            float* __restrict__ out, const int* gate, int gate_on) {
+  mh_pdl_sync();
   __shared__ RowStat sh[8][128];
   if (gate && ((*reinterpret_cast<const volatile int*>(gate) != 0) != (gate_on != 0))) return;   // guarded stash, see mh_step_forward
   const int rx = threadIdx.x, py = threadIdx.y;
@@ -271,10 +275,10 @@ int mh_merge_stats_impl(const float* stats_in, int64_t n_parts, int64_t B, int64
   int64_t nblk = (n_parts >= 256) ? MH_MERGE_BLOCKS : 1;
   if (nblk > 1) {
     MH_CHECK_ARG(scratch, "scratch required for large merges");
-    merge_stats_kernel<<<dim3(gx, (unsigned)nblk), block, 0, st>>>(stats_in, n_parts, lds_, scratch, gate, gate_on);
-    merge_stats_kernel<<<dim3(gx, 1), block, 0, st>>>(scratch, nblk, lds_, stats_out, gate, gate_on);
+    mh_launch(merge_stats_kernel, dim3(gx, (unsigned)nblk), block, 0, st, stats_in, n_parts, lds_, scratch, gate, gate_on);
+    mh_launch(merge_stats_kernel, dim3(gx, 1), block, 0, st, scratch, nblk, lds_, stats_out, gate, gate_on);
   } else {
-    merge_stats_kernel<<<dim3(gx, 1), block, 0, st>>>(stats_in, n_parts, lds_, stats_out, gate, gate_on);
+    mh_launch(merge_stats_kernel, dim3(gx, 1), block, 0, st, stats_in, n_parts, lds_, stats_out, gate, gate_on);
   }
   MH_LAUNCH_OK();
   return MH_OK;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __rest
                                                              int64_t ldo, float* __restrict__ scalars,
                                                              const float* __restrict__ state, float guard_min_l,
                                                              int* __restrict__ guard_flag, const int* gate, int gate_on) {
+  mh_pdl_sync();
   __shared__ double sh[3][32];
   if (gate && ((*reinterpret_cast<const volatile int*>(gate) != 0) != (gate_on != 0))) return;   // guarded stash, see mh_step_forward
   double sl = 0.0, s1 = 0.0, s5 = 0.0;
@@ -351,7 +356,7 @@ int mh_finalize_rows_impl(const float* stats, int64_t lds_, const float* rowp, i
                           int* guard_flag, const int* gate, int gate_on, void* stream) {
   MH_CHECK_ARG(stats && rowp && rowout && scalars, "null pointer");
   MH_CHECK_ARG(B > 0 && B_total >= B && lds_ >= B && ldp >= B && ldo >= B, "bad shape");
-  finalize_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stats, lds_, rowp, ldp, B, B_total, sphere, rowout, ldo,
+  mh_launch(finalize_rows_kernel, 1, 1024, 0, (cudaStream_t)stream, stats, lds_, rowp, ldp, B, B_total, sphere, rowout, ldo,
                                                              scalars, state, guard_min_l, guard_flag, gate, gate_on);
   MH_LAUNCH_OK();
   return MH_OK;
@@ -390,6 +395,7 @@ __global__ void __launch_bounds__(256) norm_backward_x_kernel(const float* __res
                                                               const float* __restrict__ aux1,
                                                               const float* __restrict__ gscal, int64_t B,
                                                               T* __restrict__ dx) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -431,13 +437,13 @@ extern "C" int mh_norm_backward_x(const float* dxhat, int n_split, int64_t split
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((B + 7) / 8));
   if (x_dtype == MH_F32)
-    norm_backward_x_kernel<float><<<grid, 256, 0, st>>>(dxhat, n_split, split_stride, x_hat32, xnorm, rowp, ldp, aux0,
+    mh_launch(norm_backward_x_kernel<float>, grid, 256, 0, st, dxhat, n_split, split_stride, x_hat32, xnorm, rowp, ldp, aux0,
                                                         aux1, gscal, B, (float*)dx);
   else if (x_dtype == MH_BF16)
-    norm_backward_x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dxhat, n_split, split_stride, x_hat32, xnorm, rowp, ldp,
+    mh_launch(norm_backward_x_kernel<__nv_bfloat16>, grid, 256, 0, st, dxhat, n_split, split_stride, x_hat32, xnorm, rowp, ldp,
                                                                 aux0, aux1, gscal, B, (__nv_bfloat16*)dx);
   else if (x_dtype == MH_F16)
-    norm_backward_x_kernel<__half><<<grid, 256, 0, st>>>(dxhat, n_split, split_stride, x_hat32, xnorm, rowp, ldp, aux0,
+    mh_launch(norm_backward_x_kernel<__half>, grid, 256, 0, st, dxhat, n_split, split_stride, x_hat32, xnorm, rowp, ldp, aux0,
                                                          aux1, gscal, B, (__half*)dx);
   else
     MH_CHECK_ARG(false, "unknown dtype");
@@ -465,6 +471,7 @@ __global__ void __launch_bounds__(256) norm_backward_w_cd_kernel(const float* __
                                                                  const float* __restrict__ gscal,
                                                                  const float* __restrict__ class_scale, int64_t C,
                                                                  float* __restrict__ dW, int64_t ld) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= C) return;
@@ -493,6 +500,7 @@ __global__ void __launch_bounds__(256) norm_backward_w_dc_kernel(const float* __
                                                                  const float* __restrict__ gscal,
                                                                  const float* __restrict__ class_scale, int64_t C,
                                                                  float* __restrict__ dW, int64_t ld) {
+  mh_pdl_sync();
   extern __shared__ float slab[];            // [512][33]
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c0 = (int64_t)blockIdx.x * 32;
@@ -537,7 +545,7 @@ extern "C" int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, c
   cudaStream_t st = (cudaStream_t)stream;
   if (layout == MH_LAYOUT_CD) {
     MH_CHECK_ARG(ld % 4 == 0 && ((uintptr_t)dW & 15) == 0, "dW must be 16-byte aligned");
-    norm_backward_w_cd_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(dw_hat, (const __nv_bfloat16*)w_hat_bf16, w_hat32,
+    mh_launch(norm_backward_w_cd_kernel, (unsigned)((C + 7) / 8), 256, 0, st, dw_hat, (const __nv_bfloat16*)w_hat_bf16, w_hat32,
                                                                       inv_norm, gscal, class_scale, C, dW, ld);
   } else if (layout == MH_LAYOUT_DC) {
     static MhDeviceOnce attr_once;
@@ -545,7 +553,7 @@ extern "C" int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, c
     MH_CUDA_OK(mh_once_per_device(attr_once, [&] {
       return cudaFuncSetAttribute(norm_backward_w_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     }));
-    norm_backward_w_dc_kernel<<<(unsigned)((C + 31) / 32), 256, smem, st>>>(dw_hat, (const __nv_bfloat16*)w_hat_bf16,
+    mh_launch(norm_backward_w_dc_kernel, (unsigned)((C + 31) / 32), 256, smem, st, dw_hat, (const __nv_bfloat16*)w_hat_bf16,
                                                                           w_hat32, inv_norm, gscal, class_scale, C, dW, ld);
   } else {
     MH_CHECK_ARG(false, "unknown layout");
@@ -560,13 +568,14 @@ extern "C" int mh_norm_backward_w(const float* dw_hat, const void* w_hat_bf16, c
 // ------------------------------------------------------------------------------------------------
 __global__ void make_gscal_kernel(const float* __restrict__ g_loss, const float* __restrict__ g_lossg, float inv_b,
                                   float* __restrict__ gscal) {
+  mh_pdl_sync();
   gscal[0] = (g_loss ? g_loss[0] : 0.f) * inv_b;
   gscal[1] = g_lossg ? g_lossg[0] : 0.f;
 }
 
 extern "C" int mh_make_gscal(const float* g_loss, const float* g_lossg, int64_t B_total, float* gscal, void* stream) {
   MH_CHECK_ARG(gscal && B_total > 0, "bad argument");
-  make_gscal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g_loss, g_lossg, 1.f / (float)B_total, gscal);
+  mh_launch(make_gscal_kernel, 1, 1, 0, (cudaStream_t)stream, g_loss, g_lossg, 1.f / (float)B_total, gscal);
   MH_LAUNCH_OK();
   return MH_OK;
 }

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) prologue_w_cd_kernel(float* __restrict__ 
                                                             __nv_bfloat16* __restrict__ what, int64_t C_pad,
                                                             float* __restrict__ what32, float* __restrict__ inv_norm,
                                                             SgdArgs sg) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= C_pad) return;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) prologue_w_dc_kernel(float* __restrict__ 
                                                             __nv_bfloat16* __restrict__ what, int64_t C_pad,
                                                             float* __restrict__ what32, float* __restrict__ inv_norm,
                                                             SgdArgs sg) {
+  mh_pdl_sync();
   extern __shared__ float slab[];            // [512][33]
   __shared__ float part[8][PW_TC];
   __shared__ float invs[PW_TC];
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(256) prologue_w_dc4_kernel(float* __restrict__
                                                              __nv_bfloat16* __restrict__ what, int64_t C_pad,
                                                              float* __restrict__ what32, float* __restrict__ inv_norm,
                                                              SgdArgs sg) {
+  mh_pdl_sync();
   // [512 d][8 chunks of 4 classes], 128 B per d-row; chunk q of row d sits at position q ^ ((d >> 1) & 7), which makes
   // both the 16-byte stores of the load phase (8 lanes = 8 chunks of one row) and the 16-byte column reads of the write
   // phase (8 lanes = one chunk of 8 row pairs) conflict-free.  (4-byte accesses into a [512][33] slab kept the
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(256, 1) prologue_w_dc4p_kernel(const float* __
                                                                  __nv_bfloat16* __restrict__ what, int64_t C_pad,
                                                                  float* __restrict__ what32, float* __restrict__ inv_norm,
                                                                  int64_t n_tiles) {
+  mh_pdl_sync();
   extern __shared__ float4 slab4[];            // PW_NST x [512 d][8 chunks], chunk q of row d at q ^ ((d >> 1) & 7)
   __shared__ float part[8][PW_TC];
   __shared__ __align__(16) float invs[PW_TC];
@@ -391,6 +395,7 @@ __global__ void __launch_bounds__(256, 1) prologue_w_dc4p_kernel(const float* __
 
 // zero the padding rows [C, C_pad) that no DC block covers
 __global__ void zero_pad_rows_kernel(__nv_bfloat16* what, int64_t row0, int64_t row1) {
+  mh_pdl_sync();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t n = (row1 - row0) * MH_D;
   if (i < n) what[row0 * MH_D + i] = __float2bfloat16(0.f);
@@ -402,7 +407,7 @@ static int launch_prologue_w(float* W, int layout, int64_t C, int64_t ld, void* 
   if (layout == MH_LAYOUT_CD) {
     MH_CHECK_ARG(ld >= MH_D && ld % 4 == 0, "CD layout needs ld >= 512 and ld % 4 == 0");
     dim3 grid((unsigned)((C_pad + 7) / 8));
-    prologue_w_cd_kernel<SGD><<<grid, 256, 0, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
+    mh_launch(prologue_w_cd_kernel<SGD>, grid, 256, 0, st, W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
   } else if (layout == MH_LAYOUT_DC) {
     MH_CHECK_ARG(ld >= C, "DC layout needs ld >= C");
     static MhDeviceOnce attr_once;
@@ -421,15 +426,15 @@ static int launch_prologue_w(float* W, int layout, int64_t C, int64_t ld, void* 
       const int n_sm = mh_num_sms();
       const int64_t n_tiles = grid.x;
       const unsigned nb = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
-      prologue_w_dc4p_kernel<<<nb, 256, smem_p, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, n_tiles);
+      mh_launch(prologue_w_dc4p_kernel, nb, 256, smem_p, st, W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, n_tiles);
     } else if (vec4)
-      prologue_w_dc4_kernel<SGD><<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
+      mh_launch(prologue_w_dc4_kernel<SGD>, grid, 256, smem, st, W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
     else
-      prologue_w_dc_kernel<SGD><<<grid, 256, smem, st>>>(W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
+      mh_launch(prologue_w_dc_kernel<SGD>, grid, 256, smem, st, W, C, ld, (__nv_bfloat16*)w_hat_bf16, C_pad, w_hat32, inv_norm, sg);
     const int64_t covered = (int64_t)grid.x * PW_TC;
     if (covered < C_pad) {
       int64_t n = (C_pad - covered) * MH_D;
-      zero_pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)w_hat_bf16, covered, C_pad);
+      mh_launch(zero_pad_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (__nv_bfloat16*)w_hat_bf16, covered, C_pad);
     }
   } else {
     MH_CHECK_ARG(false, "unknown layout");
@@ -468,6 +473,7 @@ extern "C" int mh_sgd_step_w(float* W, int layout, int64_t C, int64_t ld, const 
 __global__ void __launch_bounds__(256) vpl_mix_kernel(const __nv_bfloat16* __restrict__ what, const float* __restrict__ mem,
                                                       const float* __restrict__ life, float lamda, int64_t C, int64_t C_pad,
                                                       __nv_bfloat16* __restrict__ v, float* __restrict__ alpha) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= C_pad) return;
@@ -508,7 +514,7 @@ extern "C" int mh_vpl_mix(const void* w_hat_bf16, const float* mem, const float*
   MH_CHECK_ARG(w_hat_bf16 && mem && life && v_bf16 && alpha_out, "null pointer");
   MH_CHECK_ARG(C > 0 && C_pad >= C, "bad shape");
   MH_CHECK_ARG(((uintptr_t)mem & 15) == 0 && ((uintptr_t)w_hat_bf16 & 7) == 0 && ((uintptr_t)v_bf16 & 7) == 0, "alignment");
-  vpl_mix_kernel<<<(unsigned)((C_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  mh_launch(vpl_mix_kernel, (unsigned)((C_pad + 7) / 8), 256, 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)w_hat_bf16, mem, life, lamda, C, C_pad, (__nv_bfloat16*)v_bf16, alpha_out);
   MH_LAUNCH_OK();
   return MH_OK;
@@ -535,6 +541,7 @@ __global__ void __launch_bounds__(256) prologue_x_kernel(const T* __restrict__ x
                                                          __nv_bfloat16* __restrict__ xhat, float* __restrict__ xhat32,
                                                          float* __restrict__ xnorm, float* __restrict__ t_raw,
                                                          int32_t* __restrict__ label_local, int64_t c_total) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B_pad) return;
@@ -612,13 +619,13 @@ extern "C" int mh_prologue_x(const void* x, int x_dtype, int64_t B, int64_t B_pa
   dim3 grid((unsigned)((B_pad + 7) / 8));
   __nv_bfloat16* xh = (__nv_bfloat16*)x_hat_bf16;
   if (x_dtype == MH_F32)
-    prologue_x_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
+    mh_launch(prologue_x_kernel<float>, grid, 256, 0, st, (const float*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
                                                    inv_norm, xh, x_hat32, xnorm, t_raw, label_local, c_total);
   else if (x_dtype == MH_BF16)
-    prologue_x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, B_pad, labels, W, layout, C, ld,
+    mh_launch(prologue_x_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, B, B_pad, labels, W, layout, C, ld,
                                                            c_offset, inv_norm, xh, x_hat32, xnorm, t_raw, label_local, c_total);
   else if (x_dtype == MH_F16)
-    prologue_x_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
+    mh_launch(prologue_x_kernel<__half>, grid, 256, 0, st, (const __half*)x, B, B_pad, labels, W, layout, C, ld, c_offset,
                                                     inv_norm, xh, x_hat32, xnorm, t_raw, label_local, c_total);
   else
     MH_CHECK_ARG(false, "unknown x dtype");
@@ -667,6 +674,7 @@ __global__ void __launch_bounds__(1024) row_params_kernel(MhParams p, int64_t B,
                                                           const float* __restrict__ t_raw,
                                                           const float* __restrict__ margins, float* state,
                                                           int update_state, float* __restrict__ rowp, int64_t ldp) {
+  mh_pdl_sync();
   __shared__ double sh[32];
   __shared__ float bc[4];
   const float PI = 3.14159265358979323846f;
@@ -849,7 +857,7 @@ extern "C" int mh_row_params(const mh_config* cfg_host, int64_t B, const float* 
   MH_CHECK_ARG((p.family != MH_ELASTIC_COS && p.family != MH_ELASTIC_ARC && p.family != MH_VPL_ARC) || margins,
                "ElasticFace / VPL-ArcFace need the per-row margins / interpolation weights");
   MH_CHECK_ARG(p.family != MH_SPHEREFACE || (p.sphere_m >= 0 && p.sphere_m <= 5), "SphereFace m must be in 0..5");
-  row_params_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p, B, xnorm, t_raw, margins, state, update_state, rowp, ldp);
+  mh_launch(row_params_kernel, 1, 1024, 0, (cudaStream_t)stream, p, B, xnorm, t_raw, margins, state, update_state, rowp, ldp);
   MH_LAUNCH_OK();
   return MH_OK;
 }

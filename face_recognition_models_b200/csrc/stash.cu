@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) stash_prep_kernel(const float* __restrict
                                                          float umax, __nv_bfloat16* __restrict__ xs,
                                                          float* __restrict__ rho, float* __restrict__ gty,
                                                          const int* __restrict__ fallback) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B_pad) return;
@@ -57,7 +58,7 @@ int mh_stash_prep_impl(const mh_config* cfg_host, const float* rowp, int64_t ldp
   MH_CHECK_ARG(cfg_host && rowp && rowout && x_hat32 && xs_bf16 && rho && gty, "null pointer");
   MH_CHECK_ARG(B > 0 && B_pad >= B && ldp >= B && ldo >= B, "bad shape");
   const MhParams p = mh_make_params(cfg_host);
-  stash_prep_kernel<<<(unsigned)((B_pad + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  mh_launch(stash_prep_kernel, (unsigned)((B_pad + 7) / 8), 256, 0, (cudaStream_t)stream, 
       rowp, ldp, rowout, ldo, x_hat32, B, B_pad, mh_family_umax(&p), (__nv_bfloat16*)xs_bf16, rho, gty, fallback);
   MH_LAUNCH_OK();
   return MH_OK;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) stash_dx_combine_kernel(const float* __re
                                                                const int32_t* __restrict__ label_local,
                                                                const __nv_bfloat16* __restrict__ what, int64_t B,
                                                                float* __restrict__ out) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -100,7 +102,7 @@ extern "C" int mh_stash_dx_combine(const float* dxhat_part, int n_split, int64_t
   MH_CHECK_ARG(dxhat_part && dxhat, "null pointer");
   MH_CHECK_ARG(!rho || (gty && label_local && w_hat_bf16), "the stash terms need rho, gty, label_local and w_hat together");
   MH_CHECK_ARG(n_split >= 1 && B > 0, "bad shape");
-  stash_dx_combine_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  mh_launch(stash_dx_combine_kernel, (unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream, 
       dxhat_part, n_split, split_stride, rho, gty, label_local, (const __nv_bfloat16*)w_hat_bf16, B, dxhat);
   MH_LAUNCH_OK();
   return MH_OK;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(256) stash_dw_target_kernel(const float* __res
                                                               const float* __restrict__ inv_norm,
                                                               const float* __restrict__ gscal, int64_t B, int layout,
                                                               float* __restrict__ dW, int64_t ld) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -207,7 +210,7 @@ extern "C" int mh_stash_dw_target(const float* gty, const int32_t* label_local, 
   MH_CHECK_ARG(layout == MH_LAYOUT_CD || layout == MH_LAYOUT_DC, "unknown layout");
   MH_CHECK_ARG(layout != MH_LAYOUT_CD || (ld % 4 == 0 && ((uintptr_t)dW & 15) == 0), "CD dW must be 16-byte aligned");
   MH_CHECK_ARG(((uintptr_t)label_local & 15) == 0, "label_local must be 16-byte aligned");
-  stash_dw_target_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  mh_launch(stash_dw_target_kernel, (unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream, 
       gty, label_local, x_hat32, (const __nv_bfloat16*)w_hat_bf16, inv_norm, gscal, B, layout, dW, ld);
   MH_LAUNCH_OK();
   return MH_OK;

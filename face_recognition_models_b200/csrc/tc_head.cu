@@ -737,6 +737,9 @@ __device__ __forceinline__ void tc_body(const CUtensorMap& tmA, const CUtensorMa
   if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   cluster_sync_all();
+  // barriers, TMEM and tensor-map prefetch above touch nothing a predecessor writes: with programmatic dependent launch
+  // they overlap the previous kernel's tail; every global / TMA access of every role comes after this point
+  mh_pdl_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -1210,7 +1213,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  if (gate_closed(a.gate, a.gate_on)) return;
+  if (a.gate) {                       // gated launch (guarded stash): the flag is a predecessor's output, decide first
+    mh_pdl_sync();
+    if (gate_closed(a.gate, a.gate_on)) return;
+  }
   tc_body<MODE, V>(tmA, tmB, a, blockIdx.x >> 1, gridDim.x >> 1, smem_raw);   // tile-scheduling unit: CTA pair
 }
 
@@ -1369,6 +1375,7 @@ template <int MODE, int V>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel_pwfwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmW32, const PwArgs pw, const int n_pw) {
+  mh_pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   const int64_t pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
   if (pair < n_pw) pw_role(pw, &tmW32, (int)blockIdx.x, 2 * n_pw, smem_raw);
@@ -1427,13 +1434,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& args, cud
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see mh_launch (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = mh_pdl_enabled() ? 2 : 1;
   MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel<MODE, V>, ta, tb, args));
   return MH_OK;
 }
@@ -1482,6 +1491,7 @@ extern "C" int64_t mh_fwd_num_tiles(int64_t C_pad) { (void)C_pad; return 2 * (in
 
 // records of rows a pair never visits stay at the merge identity (max = -inf, sums = 0)
 __global__ void stats_identity_kernel(float* __restrict__ st, int64_t n_parts, int64_t B_pad, const int* gate, int gate_on) {
+  mh_pdl_sync();
   if (gate_closed(gate, gate_on)) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = n_parts * MH_ST_PLANES * B_pad;
@@ -1553,7 +1563,7 @@ static int launch_s_tiles(const mh_config* cfg_host, const void* x_hat_bf16, int
   const int64_t rows_per_launch = (int64_t)units * BMT;
   if (stats_tiles) {
     const int64_t n = 2 * (int64_t)units * MH_ST_PLANES * B_pad;
-    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * units, B_pad, gate, gate_on);
+    mh_launch(stats_identity_kernel, (unsigned)((n + 255) / 256), 256, 0, st, stats_tiles, 2 * units, B_pad, gate, gate_on);
   }
   for (int64_t r0 = 0; r0 < B_pad; r0 += rows_per_launch) {
     const int64_t rows = std::min(rows_per_launch, B_pad - r0);
@@ -1845,13 +1855,15 @@ extern "C" int mh_tc_backward_dxdw(const void* G_bf16, int64_t B_pad, int64_t C,
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see mh_launch (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = mh_pdl_enabled() ? 2 : 1;
   const int n_dx = m_tiles * n_split;
   MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel_dxdw, ta_dx, tb_dx, ax, ta_dw, tb_dw, aw, n_dx));
   return MH_OK;
@@ -1886,13 +1898,15 @@ static int launch_pwfwd(const CUtensorMap& ta, const CUtensorMap& tb, const TcAr
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see mh_launch (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = mh_pdl_enabled() ? 2 : 1;
   MH_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_kernel_pwfwd<MODE, V>, ta, tb, args, tw32, pw, n_pw));
   return MH_OK;
 }
@@ -1934,7 +1948,7 @@ extern "C" int mh_tc_forward_pw(const mh_config* cfg_host, const void* x_hat_bf1
   MH_CUDA_OK(cudaMemsetAsync(ready_ws, 0, sizeof(int) * (size_t)(n_ct + 1), st));
   {
     const int64_t n = 2 * (int64_t)pairs * MH_ST_PLANES * B_pad;
-    stats_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stats_tiles, 2 * pairs, B_pad, nullptr, 0);
+    mh_launch(stats_identity_kernel, (unsigned)((n + 255) / 256), 256, 0, st, stats_tiles, 2 * pairs, B_pad, nullptr, 0);
   }
   CUtensorMap ta, tb;
   if (int e = make_tmap(&tb, w_hat_bf16, C_pad, MH_D, BN / 2)) return e;

@@ -15,6 +15,7 @@ __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v)
 template <typename T>
 __global__ void __launch_bounds__(256) pair_cosine_kernel(const T* __restrict__ e1, const T* __restrict__ e2, int64_t N,
                                                           int64_t d, int64_t ld1, int64_t ld2, float* __restrict__ out) {
+  mh_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -54,12 +55,12 @@ extern "C" int mh_pair_cosine(const void* e1, const void* e2, int dtype, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((N + 7) / 8));
   if (dtype == MH_F32)
-    pair_cosine_kernel<float><<<grid, 256, 0, st>>>((const float*)e1, (const float*)e2, N, d, ld1, ld2, cos_out);
+    mh_launch(pair_cosine_kernel<float>, grid, 256, 0, st, (const float*)e1, (const float*)e2, N, d, ld1, ld2, cos_out);
   else if (dtype == MH_BF16)
-    pair_cosine_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)e1, (const __nv_bfloat16*)e2, N, d, ld1,
+    mh_launch(pair_cosine_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)e1, (const __nv_bfloat16*)e2, N, d, ld1,
                                                             ld2, cos_out);
   else if (dtype == MH_F16)
-    pair_cosine_kernel<__half><<<grid, 256, 0, st>>>((const __half*)e1, (const __half*)e2, N, d, ld1, ld2, cos_out);
+    mh_launch(pair_cosine_kernel<__half>, grid, 256, 0, st, (const __half*)e1, (const __half*)e2, N, d, ld1, ld2, cos_out);
   else
     MH_CHECK_ARG(false, "unknown dtype");
   MH_LAUNCH_OK();

@@ -365,6 +365,10 @@ class HeadEngine:
             scratch = self._buf("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev)
             if want_grad and self.stash_ok():
                 stash = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
+            elif want_grad and self.backward_mode == "stash":
+                raise L.MarginHeadError("backward_mode='stash' on a head that only passes mh_tc_stash_guarded_ok needs the "
+                                        "whole-phase entry points (single GPU, MH_STEP_API=1): the guarded stash is sequenced "
+                                        "in csrc/step.cu")
             L.call("mh_tc_forward", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_gemm), Cn, C_pad, _ptr(rowp), B_pad,
                    _ptr(label_local), _ptr(state), _ptr(stats_tiles), _ptr(stash), st)
             L.call("mh_merge_stats", _ptr(stats_tiles), n_tiles, B, B_pad, _ptr(scratch), _ptr(stats), st)

@@ -97,6 +97,14 @@ class _MarginHeadBase(nn.Module):
         if labels.shape[0] != feats.shape[0]:
             raise ValueError("feats / labels batch mismatch")
 
+    def prefetch(self) -> None:
+        """Enqueue the W prologue of the NEXT forward now, on the current stream.  It depends on the class centres only, not
+        on the batch, so a training loop can call this before the batch's host-to-device copy or before / beside the
+        backbone forward (on a side stream: the prologue is HBM-bound, the backbone tensor-bound) and the head's forward
+        then starts with its GEMM.  Good for exactly one forward; any write to the parameter in between invalidates it
+        (storage + version counter), and the forward then simply runs its own prologue."""
+        self._engine.prefetch_w(self._param())
+
     def fused_loss(self, feats: torch.Tensor, labels: torch.Tensor) -> FusedOutput:
         self._check(feats, labels)
         self._pre_forward(feats)
@@ -368,6 +376,14 @@ class VPLArcFace(_MarginHeadBase):
         self.mem[uniq] = mean
         self.life[uniq] = float(self.delta)
         self.life.sub_(1.0)
+
+    def prefetch(self) -> None:
+        """Enqueue the W prologue of the NEXT forward now, on the current stream.  It depends on the class centres only, not
+        on the batch, so a training loop can call this before the batch's host-to-device copy or before / beside the
+        backbone forward (on a side stream: the prologue is HBM-bound, the backbone tensor-bound) and the head's forward
+        then starts with its GEMM.  Good for exactly one forward; any write to the parameter in between invalidates it
+        (storage + version counter), and the forward then simply runs its own prologue."""
+        self._engine.prefetch_w(self._param())
 
     def fused_loss(self, feats: torch.Tensor, labels: torch.Tensor) -> FusedOutput:
         self._check(feats, labels)

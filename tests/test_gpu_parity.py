@@ -227,8 +227,9 @@ def ctypes_cfg(head):
     return C.byref(head._engine.cfg)
 
 
-def test_stash_eligibility_and_override(pkg):
-    """auto = stash only when the fixed-reference softmax is provably safe; forcing it elsewhere raises."""
+def test_stash_eligibility_and_override(pkg, monkeypatch):
+    """auto = the proven stash only when the fixed-reference softmax is provably safe; elsewhere the guarded stash (step API)
+    or the recompute backward."""
     lib = pkg._lib.load()
     arc = pkg.ArcFace(512, 1000, s=64.0, m=0.5, easy_margin=False).cuda()
     assert arc._engine.stash_ok()
@@ -243,9 +244,17 @@ def test_stash_eligibility_and_override(pkg):
     assert lib.mh_tc_fixref_ok(ctypes_cfg(mv), 1000) == 1
     for h in (pkg.CosFace(512, 1000), pkg.AdaFace(512, 1000), pkg.MagFace(512, 1000), pkg.ElasticArcFace(512, 1000)):
         assert h.cuda()._engine.stash_ok()
+    # forcing the stash on such a head selects the GUARDED stash of the step API (tests/test_gpu_guarded_stash.py) ...
+    for h in (big, sph, cur):
+        assert lib.mh_tc_stash_guarded_ok(ctypes_cfg(h), 1000) == 1 and lib.mh_tc_stash_guarded_ok(ctypes_cfg(arc), 1000) == 0
     sph.backward_mode = "stash"
+    out = sph.fused_loss(torch.randn(4, 512, device="cuda", requires_grad=True), torch.zeros(4, dtype=torch.long, device="cuda"))
+    assert torch.isfinite(out.loss) and int(sph._engine._step_T["guard"].item()) == 0
+    # ... which the entry-point-by-entry-point driver does not sequence: there it raises instead of silently recomputing
+    monkeypatch.setenv("MH_STEP_API", "0")
     with pytest.raises(pkg._lib.MarginHeadError):
         sph.fused_loss(torch.randn(4, 512, device="cuda", requires_grad=True), torch.zeros(4, dtype=torch.long, device="cuda"))
+    monkeypatch.delenv("MH_STEP_API")
     # the s = 128 head still trains, through the online-max forward + recompute backward
     cfg = mo.HeadConfig.default("arcface")
     cfg.s = 128.0

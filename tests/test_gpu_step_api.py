@@ -142,3 +142,36 @@ def test_merged_backward_at_multi_gpu_row_counts(B):
     assert cosine(x.grad, dx) >= 0.9995 and cosine(head.weight.grad, dW) >= 0.9995
     assert abs(float(x.grad.norm()) / float(dx.norm()) - 1.0) <= 2e-3
     assert abs(float(head.weight.grad.norm()) / float(dW.norm()) - 1.0) <= 2e-3
+
+
+def test_prefetch_runs_the_prologue_ahead_and_never_serves_a_stale_one():
+    """head.prefetch(): the W prologue of the next forward enqueued early (before the batch copy / beside the backbone).
+    Same bits as without it; a parameter update between prefetch and forward invalidates it."""
+    import face_recognition_models_b200 as pkg
+    g = torch.Generator(device="cuda").manual_seed(3)
+    head = pkg.ArcFace(512, 30_011).cuda()
+    x = torch.randn(200, 512, device="cuda", generator=g)
+    y = torch.randint(0, 30_011, (200,), device="cuda", generator=g)
+
+    def step(prefetch, update=False):
+        head.weight.grad = None
+        if prefetch:
+            head.prefetch()
+        if update:
+            with torch.no_grad():
+                head.weight.mul_(1.0 + torch.linspace(0, 1, 30_011, device="cuda").unsqueeze(1))   # changes every direction's norm, and w_0 .. w_C differently
+                head.weight[:, 0] += 0.05
+        xg = x.detach().requires_grad_(True)
+        out = head.fused_loss(xg, y)
+        out.loss.backward()
+        return out.loss.detach().clone(), xg.grad.clone(), head.weight.grad.clone()
+
+    a = step(False)
+    b = step(True)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    c = step(True, update=True)           # prologue prefetched for the OLD weights, then the weights change
+    d = step(False)                       # reference: plain step on the new weights
+    assert not torch.equal(a[0], c[0])
+    for u, v in zip(c, d):
+        assert torch.equal(u, v)

@@ -93,6 +93,7 @@ class ClockSampler:
         self.samples = []          # (sm_mhz, sm_max_mhz, power_w, set(reasons))
         self.proc = None
         self.active = False
+        self.armed = False         # set by the bench around the arms that count: timed() then switches `active` on and off
         self._stop = False
         self._t = None
         self._nvml = None
@@ -526,6 +527,16 @@ def run_b200(args):
         working sets: one event pair around the K steps.  Small ones: the L2 is flushed (256 MB write) before every
         step, outside that step's event pair, and the K per-step times are summed."""
         barrier()
+        was_active = sampler.active if sampler else False
+        if sampler and sampler.armed:
+            sampler.active = True                         # clocks are sampled inside the timed regions only (not the idle gaps)
+        try:
+            return _timed_region(fn, steps)
+        finally:
+            if sampler:
+                sampler.active = was_active
+
+    def _timed_region(fn, steps):
         if flush is None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -628,11 +639,15 @@ def run_b200(args):
         torch.cuda.synchronize()
         loss_val = float(out.loss.detach())
         if sampler:
-            sampler.active = True
+            sampler.armed = True
         # ---- device-resident arm -----------------------------------------------------------------------------------
-        ms = arm(step_resident, args.steps)
-        # ---- end-to-end arm (host buffers): same protocol -------------------------------------------------------------
-        ms_e2e = arm(step_e2e, args.steps)
+        if os.environ.get("BENCH_E2E_FIRST") == "1":      # diagnostic: does the order of the arms matter on this box?
+            ms_e2e = arm(step_e2e, args.steps)
+            ms = arm(step_resident, args.steps)
+        else:
+            ms = arm(step_resident, args.steps)
+            # ---- end-to-end arm (host buffers): same protocol ---------------------------------------------------------
+            ms_e2e = arm(step_e2e, args.steps)
         # ---- the same K steps again with CUDA events around every C-ABI entry point on the launching stream (the
         # product path issues a step as two calls, mh_step_forward / mh_step_backward; MH_STEP_API=0 drives the same
         # kernels one entry point at a time so that each can be timed): feeds `kernels` and `roofline`, not `value`
@@ -664,7 +679,7 @@ def run_b200(args):
         else:
             alt_ok = False
         if sampler:
-            sampler.active = False
+            sampler.armed = False
         kern = {}
         for name, e0, e1, launches in prof:
             k = kern.setdefault(name, [0.0, 0, 0])

@@ -441,21 +441,21 @@ struct FwdAcc {
 
 constexpr float CNT_BIG = 1152921504606846976.f;   // 2^60
 
-template <int V>
+template <int V, bool CL = true>
 __device__ __forceinline__ float elem_u(float raw, float lo, float hi, float thr, float ha, float hb, float& c_out) {
   float c = raw;
-  if (V != V_PLAIN) c = fminf(fmaxf(raw, lo), hi);
+  if (V != V_PLAIN && CL) c = fminf(fmaxf(raw, lo), hi);
   c_out = c;
   if (V == V_MV) return (c > thr) ? fmaf(ha, c, hb) : c;
   if (V == V_CURR) return (c > thr) ? c * (ha + c) : c;
   return c;
 }
-template <int V>
+template <int V, bool CL = true>
 __device__ __forceinline__ float elem_du(float raw, float c, float thr, float ha) {
   float du = 1.f;
   if (V == V_MV) du = (c > thr) ? ha : 1.f;
   if (V == V_CURR) du = (c > thr) ? (ha + 2.f * c) : 1.f;
-  if (V != V_PLAIN && c != raw) du = 0.f;            // clamp passes gradient only inside [lo, hi]
+  if (V != V_PLAIN && CL && c != raw) du = 0.f;      // clamp passes gradient only inside [lo, hi]
   return du;
 }
 
@@ -531,7 +531,16 @@ __device__ __forceinline__ void fwd_chunk(uint32_t (&v)[32], int col0, int nvali
 template <int V, bool STASH>
 __device__ __forceinline__ void fwd_chunk_fix(const uint32_t (&v)[32], int col0, int nvalid, const RowCtx& rc, float lo,
                                               float hi, float ha, float hb, FwdAcc& acc, uint32_t (&pk)[16]) {
-  const bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid) || (STASH && !rc.valid);
+  bool slow = (rc.tcol >= col0 && rc.tcol < col0 + 32) || (col0 + 32 > nvalid) || (STASH && !rc.valid);
+  if (V != V_PLAIN && !slow) {
+    // Clamped families: a cosine outside [lo, hi] needs near-duplicate vectors, so instead of clamping every element (two
+    // FMNMX, plus a compare + select for the clamp's gradient mask) the chunk takes one max-|raw| pass (one FMNMX with a
+    // free |.| modifier per element) and goes to the rare path, which clamps, if anything is out of range.
+    float am = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) am = fmaxf(am, fabsf(__uint_as_float(v[k])));
+    slow = am > fminf(-lo, hi);
+  }
   if (!slow) {
     float l2[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f}, z2[2] = {0.f, 0.f};
 #pragma unroll
@@ -541,12 +550,12 @@ __device__ __forceinline__ void fwd_chunk_fix(const uint32_t (&v)[32], int col0,
       for (int h = 0; h < 2; ++h) {
         const float raw = __uint_as_float(v[k + h]);
         float c;
-        const float u = elem_u<V>(raw, lo, hi, rc.thr, ha, hb, c);
+        const float u = elem_u<V, false>(raw, lo, hi, rc.thr, ha, hb, c);
         c2[h] += __saturatef(fmaf(c, CNT_BIG, rc.ntbig));
         const float e = ex2(fmaf(u, rc.scale2, rc.nref2));
         l2[h] += e;
         if (V == V_SPHERE) z2[h] = fmaf(e, u, z2[h]);
-        es[h] = STASH ? e * elem_du<V>(raw, c, rc.thr, ha) : e;
+        es[h] = STASH ? e * elem_du<V, false>(raw, c, rc.thr, ha) : e;
       }
       if (STASH) pk[k >> 1] = pack_bf16(es[0], es[1]);
     }

@@ -84,6 +84,11 @@ SIGNATURES = {
     "mh_tc_fixref_ok": [_cfgp, _i64],
     "mh_tc_stash_ok": [_cfgp, _i64],
     "mh_tc_stash_guarded_ok": [_cfgp, _i64],
+    "mh_tc_forward_ex": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp],
+    "mh_tc_backward_g_ex": [_cfgp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "mh_merge_stats_ex": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp],
+    "mh_finalize_rows_ex": [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _f32, _vp, _vp, _i32, _vp],
+    "mh_stash_prep_ex": [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     "mh_stash_prep": [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "mh_stash_dx_combine": [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "mh_stash_dw_target": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
@@ -145,9 +150,9 @@ PROFILE = None
 
 
 def _launches(name: str, args) -> int:
-    if name == "mh_merge_stats":
+    if name in ("mh_merge_stats", "mh_merge_stats_ex"):
         return 2 if int(args[1]) >= 256 else 1
-    if name == "mh_tc_forward":
+    if name in ("mh_tc_forward", "mh_tc_forward_ex"):
         return 2                      # statistics-identity fill + the tensor-core kernel
     if name == "mh_tc_backward_dx":
         return 0 if not getattr(args[4], "value", None) else 1

@@ -113,25 +113,6 @@ MhParams mh_make_params(const mh_config* c);
 // Upper bound of u = z / scale over non-target columns, per family (fixed-reference softmax, see mh_tc_fixref_ok).
 float mh_family_umax(const MhParams* p);
 
-// Internal (not exported) forms of entry points that the guarded stash of csrc/step.cu needs with a device-side gate:
-// the launch does nothing unless (*gate != 0) == (gate_on != 0); gate == NULL always runs (the extern "C" wrappers).
-int mh_tc_forward_impl(const mh_config* cfg, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
-                       int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
-                       const float* state, float* stats_tiles, void* stash_bf16, int stash_kind, const int* gate,
-                       int gate_on, void* stream);
-int mh_tc_backward_g_impl(const mh_config* cfg, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
-                          int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
-                          const float* state, const float* lse2, void* G_bf16, float* r_colsum, const int* gate,
-                          int gate_on, void* stream);
-int mh_merge_stats_impl(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds_, float* scratch, float* stats_out,
-                        const int* gate, int gate_on, void* stream);
-int mh_finalize_rows_impl(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B, int64_t B_total,
-                          int sphere, float* rowout, int64_t ldo, float* scalars, const float* state, float guard_min_l,
-                          int* guard_flag, const int* gate, int gate_on, void* stream);
-int mh_stash_prep_impl(const mh_config* cfg, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
-                       const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty,
-                       const int* fallback, void* stream);
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

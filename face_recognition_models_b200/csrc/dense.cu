@@ -263,10 +263,10 @@ __global__ void __launch_bounds__(1024) merge_stats_kernel(const float* __restri
 
 extern "C" int mh_merge_stats(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds_, float* scratch,
                               float* stats_out, void* stream) {
-  return mh_merge_stats_impl(stats_in, n_parts, B, lds_, scratch, stats_out, nullptr, 0, stream);
+  return mh_merge_stats_ex(stats_in, n_parts, B, lds_, scratch, stats_out, nullptr, 0, stream);
 }
 
-int mh_merge_stats_impl(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds_, float* scratch, float* stats_out,
+extern "C" int mh_merge_stats_ex(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds_, float* scratch, float* stats_out,
                         const int* gate, int gate_on, void* stream) {
   MH_CHECK_ARG(stats_in && stats_out && n_parts > 0 && lds_ >= B, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -345,13 +345,13 @@ __global__ void __launch_bounds__(1024) finalize_rows_kernel(const float* __rest
 extern "C" int mh_finalize_rows(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B,
                                 int64_t B_total, int sphere, float* rowout, int64_t ldo, float* scalars,
                                 const float* state, void* stream) {
-  return mh_finalize_rows_impl(stats, lds_, rowp, ldp, B, B_total, sphere, rowout, ldo, scalars, state, 0.f, nullptr,
+  return mh_finalize_rows_ex(stats, lds_, rowp, ldp, B, B_total, sphere, rowout, ldo, scalars, state, 0.f, nullptr,
                                nullptr, 0, stream);
 }
 
 // guard_flag != NULL: also decide whether the fixed-reference sums can be trusted (every row sum >= guard_min_l) and write
 // 0 / 1 to *guard_flag.  gate: the whole launch is a no-op unless (*gate != 0) == (gate_on != 0).
-int mh_finalize_rows_impl(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B, int64_t B_total,
+extern "C" int mh_finalize_rows_ex(const float* stats, int64_t lds_, const float* rowp, int64_t ldp, int64_t B, int64_t B_total,
                           int sphere, float* rowout, int64_t ldo, float* scalars, const float* state, float guard_min_l,
                           int* guard_flag, const int* gate, int gate_on, void* stream) {
   MH_CHECK_ARG(stats && rowp && rowout && scalars, "null pointer");

@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(256) stash_prep_kernel(const float* __restrict
 extern "C" int mh_stash_prep(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
                              const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty,
                              void* stream) {
-  return mh_stash_prep_impl(cfg_host, rowp, ldp, rowout, ldo, x_hat32, B, B_pad, xs_bf16, rho, gty, nullptr, stream);
+  return mh_stash_prep_ex(cfg_host, rowp, ldp, rowout, ldo, x_hat32, B, B_pad, xs_bf16, rho, gty, nullptr, stream);
 }
 
-int mh_stash_prep_impl(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
+extern "C" int mh_stash_prep_ex(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
                        const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty,
                        const int* fallback, void* stream) {
   MH_CHECK_ARG(cfg_host && rowp && rowout && x_hat32 && xs_bf16 && rho && gty, "null pointer");

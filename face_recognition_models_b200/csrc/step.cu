@@ -48,7 +48,7 @@ extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const
                               ws->rowp, ws->B_pad, ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr,
                               ws->pw_ready, &pw_ok, stream));
   else
-    STEP_TRY(mh_tc_forward_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+    STEP_TRY(mh_tc_forward_ex(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
                                 ws->label_local, state, ws->stats_tiles, stash ? ws->bc : nullptr, stash, nullptr, 0, stream));
   const int sphere = cfg->family == MH_SPHEREFACE ? 1 : 0;
   STEP_TRY(mh_merge_stats(ws->stats_tiles, ws->n_tiles, ws->B, ws->B_pad, ws->merge_scratch, ws->stats, stream));
@@ -60,13 +60,13 @@ extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const
   // Guarded stash: the finaliser decides on the device whether the speculative fixed-reference sums stand (every row sum
   // >= C 2^-102, see mh_tc_stash_guarded_ok) and sets ws->guard; the general forward follows as launches gated on it.
   const float guard_min_l = ldexpf((float)ws->C, -102);
-  STEP_TRY(mh_finalize_rows_impl(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, sphere, ws->rowout, ws->B_pad,
+  STEP_TRY(mh_finalize_rows_ex(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, sphere, ws->rowout, ws->B_pad,
                                  scalars, state, guard_min_l, ws->guard, nullptr, 0, stream));
-  STEP_TRY(mh_tc_forward_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+  STEP_TRY(mh_tc_forward_ex(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
                               ws->label_local, state, ws->stats_tiles, nullptr, 0, ws->guard, 1, stream));
-  STEP_TRY(mh_merge_stats_impl(ws->stats_tiles, ws->n_tiles, ws->B, ws->B_pad, ws->merge_scratch, ws->stats, ws->guard, 1,
+  STEP_TRY(mh_merge_stats_ex(ws->stats_tiles, ws->n_tiles, ws->B, ws->B_pad, ws->merge_scratch, ws->stats, ws->guard, 1,
                                stream));
-  STEP_TRY(mh_finalize_rows_impl(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, sphere, ws->rowout, ws->B_pad,
+  STEP_TRY(mh_finalize_rows_ex(ws->stats, ws->B_pad, ws->rowp, ws->B_pad, ws->B, ws->B, sphere, ws->rowout, ws->B_pad,
                                  scalars, state, 0.f, nullptr, ws->guard, 1, stream));
   return MH_OK;
 }
@@ -104,9 +104,9 @@ extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int 
     MH_CHECK_ARG(merged_split <= ws->part_splits, "dxhat_part holds fewer splits than the merged backward needs");
     if (stash) {
       if (fallback)      // guarded stash whose forward fell back: rewrite the stash with the recomputed G (no-op otherwise)
-        STEP_TRY(mh_tc_backward_g_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+        STEP_TRY(mh_tc_backward_g_ex(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
                                        ws->label_local, state, lse2, ws->bc, nullptr, fallback, 1, stream));
-      STEP_TRY(mh_stash_prep_impl(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
+      STEP_TRY(mh_stash_prep_ex(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
                                   ws->gty, fallback, stream));
       xs = ws->xs;
     } else {
@@ -130,9 +130,9 @@ extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int 
   }
   if (stash) {
     if (fallback)
-      STEP_TRY(mh_tc_backward_g_impl(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
+      STEP_TRY(mh_tc_backward_g_ex(cfg, ws->x_hat, ws->B, ws->B_pad, ws->w_hat, ws->C, ws->C_pad, ws->rowp, ws->B_pad,
                                      ws->label_local, state, lse2, ws->bc, nullptr, fallback, 1, stream));
-    STEP_TRY(mh_stash_prep_impl(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
+    STEP_TRY(mh_stash_prep_ex(cfg, ws->rowp, ws->B_pad, rowout, ws->B_pad, ws->x_hat32, ws->B, ws->B_pad, ws->xs, ws->rho,
                                 ws->gty, fallback, stream));
     xs = ws->xs;
     if (selfp) {

@@ -1601,7 +1601,7 @@ static int launch_s_tiles(const mh_config* cfg_host, const void* x_hat_bf16, int
 
 // stash_kind: 0 no stash, 1 the proven stash (mh_tc_stash_ok), 2 the guarded stash (mh_tc_stash_guarded_ok: the caller
 // checks the row sums afterwards, see mh_step_forward).  gate: see TcArgs::gate.
-int mh_tc_forward_impl(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
+extern "C" int mh_tc_forward_ex(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
                        int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
                        const float* state, float* stats_tiles, void* stash_bf16, int stash_kind, const int* gate,
                        int gate_on, void* stream) {
@@ -1624,11 +1624,11 @@ extern "C" int mh_tc_forward(const mh_config* cfg_host, const void* x_hat_bf16, 
                              const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                              const int32_t* label_local, const float* state, float* stats_tiles, void* stash_bf16,
                              void* stream) {
-  return mh_tc_forward_impl(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
+  return mh_tc_forward_ex(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state,
                             stats_tiles, stash_bf16, 1, nullptr, 0, stream);
 }
 
-int mh_tc_backward_g_impl(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
+extern "C" int mh_tc_backward_g_ex(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
                           const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                           const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
                           float* r_colsum, const int* gate, int gate_on, void* stream) {
@@ -1645,7 +1645,7 @@ extern "C" int mh_tc_backward_g(const mh_config* cfg_host, const void* x_hat_bf1
                                 const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
                                 const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
                                 float* r_colsum, void* stream) {
-  return mh_tc_backward_g_impl(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state, lse2,
+  return mh_tc_backward_g_ex(cfg_host, x_hat_bf16, B, B_pad, w_hat_bf16, C, C_pad, rowp, ldp, label_local, state, lse2,
                                G_bf16, r_colsum, nullptr, 0, stream);
 }
 

@@ -176,6 +176,8 @@ class HeadEngine:
         than its handful of gated launches (B_pad * C_pad >= 2^25); backward_mode = 'stash' takes it at any size."""
         if self._stash_ok_cached():
             return 1
+        if self.family == "vpl_arcface":           # the memory-bank heads are built on the proven stash only
+            return 0
         if self._stash_guard_val and os.environ.get("MH_STASH_GUARDED", "1") != "0":
             if self.backward_mode == "stash" or B_pad * C_pad >= GUARDED_MIN_BC:
                 return 2
@@ -349,7 +351,7 @@ class HeadEngine:
                1 if update_state else 0, _ptr(rowp), B_pad, st)
 
         stats = self._buf("stats", (L.ST_PLANES, B_pad), torch.float32, dev)
-        S = pre = logits = stash = None
+        S = pre = logits = stash = guard = None
         if exact:
             S = self._buf("S", (B, Cn), torch.float32, dev)
             # S = x_hat32 [B,512] . w_hat32^T  (w_hat32 is [C,512]: B operand strides (1, 512))
@@ -363,14 +365,15 @@ class HeadEngine:
             n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
             stats_tiles = self._buf("stats_tiles", (n_tiles, L.ST_PLANES, B_pad), torch.float32, dev)
             scratch = self._buf("merge_scratch", (L.MERGE_BLOCKS, L.ST_PLANES, B_pad), torch.float32, dev)
-            if want_grad and self.stash_ok():
+            kind = self._stash_kind(B_pad, C_pad) if want_grad else 0     # 0 none / recompute, 1 stash, 2 guarded stash
+            if self.family == "vpl_arcface" and want_grad:
+                self.stash_ok()                                           # raises on a forced but ineligible stash
+            if kind:
                 stash = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
-            elif want_grad and self.backward_mode == "stash":
-                raise L.MarginHeadError("backward_mode='stash' on a head that only passes mh_tc_stash_guarded_ok needs the "
-                                        "whole-phase entry points (single GPU, MH_STEP_API=1): the guarded stash is sequenced "
-                                        "in csrc/step.cu")
-            L.call("mh_tc_forward", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_gemm), Cn, C_pad, _ptr(rowp), B_pad,
-                   _ptr(label_local), _ptr(state), _ptr(stats_tiles), _ptr(stash), st)
+            if kind == 2:
+                guard = self._buf("stash_guard", (1,), torch.int32, dev, zero=True)
+            L.call("mh_tc_forward_ex", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_gemm), Cn, C_pad, _ptr(rowp), B_pad,
+                   _ptr(label_local), _ptr(state), _ptr(stats_tiles), _ptr(stash), kind, _ptr(None), 0, st)
             L.call("mh_merge_stats", _ptr(stats_tiles), n_tiles, B, B_pad, _ptr(scratch), _ptr(stats), st)
 
         if self.shard.world > 1:
@@ -381,9 +384,27 @@ class HeadEngine:
 
         rowout = self._buf("rowout", (L.RO_PLANES, B_pad), torch.float32, dev)
         scalars = torch.empty(4, dtype=torch.float32, device=dev)      # loss, acc@1, acc@5, loss_g (fresh: returned to the user)
-        L.call("mh_finalize_rows", _ptr(stats), B_pad, _ptr(rowp), B_pad, B, B, 1 if self.family == "sphereface" else 0,
-               _ptr(rowout), B_pad, _ptr(scalars), _ptr(state), st)
-        return dict(B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=w_hat, w_hat32=w_hat32, inv_norm=inv_norm,
+        sphere = 1 if self.family == "sphereface" else 0
+        if guard is None:
+            L.call("mh_finalize_rows", _ptr(stats), B_pad, _ptr(rowp), B_pad, B, B, sphere, _ptr(rowout), B_pad, _ptr(scalars),
+                   _ptr(state), st)
+        else:
+            # Guarded stash, sequenced here as csrc/step.cu does for one GPU: the finaliser checks the (globally merged) row
+            # sums and sets the flag -- identical on every rank, they all merged the same statistics -- and the general
+            # forward follows as launches gated on it.  The collective in between cannot be gated: it runs either way (with
+            # the gate closed it gathers the untouched statistics and the gated merge ignores the result).
+            c_tot = float(self.shard.c_total or Cn)
+            L.call("mh_finalize_rows_ex", _ptr(stats), B_pad, _ptr(rowp), B_pad, B, B, sphere, _ptr(rowout), B_pad, _ptr(scalars),
+                   _ptr(state), C.c_float(math.ldexp(c_tot, -102)), _ptr(guard), _ptr(None), 0, st)
+            L.call("mh_tc_forward_ex", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_gemm), Cn, C_pad, _ptr(rowp), B_pad,
+                   _ptr(label_local), _ptr(state), _ptr(stats_tiles), _ptr(None), 0, _ptr(guard), 1, st)
+            L.call("mh_merge_stats_ex", _ptr(stats_tiles), n_tiles, B, B_pad, _ptr(scratch), _ptr(stats), _ptr(guard), 1, st)
+            if self.shard.world > 1:
+                self.shard.comm.allgather_stats(stats, out=all_stats)
+                L.call("mh_merge_stats_ex", _ptr(all_stats), self.shard.world, B, B_pad, _ptr(scratch), _ptr(stats), _ptr(guard), 1, st)
+            L.call("mh_finalize_rows_ex", _ptr(stats), B_pad, _ptr(rowp), B_pad, B, B, sphere, _ptr(rowout), B_pad, _ptr(scalars),
+                   _ptr(state), C.c_float(0.0), _ptr(None), _ptr(guard), 1, st)
+        return dict(guard=guard, B=B, B_pad=B_pad, C_pad=C_pad, x_dtype=x.dtype, w_hat=w_hat, w_hat32=w_hat32, inv_norm=inv_norm,
                     x_hat=x_hat, x_hat32=x_hat32, xnorm=xnorm, label_local=label_local, rowp=rowp, rowout=rowout,
                     scalars=scalars, S=S, pre=pre, logits=logits, exact=exact, gen=self._gen, state=state,
                     W_shape=tuple(W.shape), ld=ld, stash=stash, w_gemm=w_gemm, vpl_alpha=alpha, t_ext=t_ext is not None)
@@ -499,7 +520,8 @@ class HeadEngine:
             return self._backward_vpl(ctx, gscal, need_dx, need_dw)
         # dW projection r_j = w^_j . dw^_j: produced beforehand by the dx side pass / the backward-G column sums (default),
         # or (MH_DW_SELFPROJ=1) taken from the dW accumulators themselves - measured break-even, see DESIGN.md 4.2
-        selfp = _selfproj()
+        guard = ctx.get("guard")                 # guarded stash: the dW GEMM always projects from its own accumulators
+        selfp = _selfproj() or guard is not None
         r_parts = B_pad // L.TILE if stash is not None else 1      # stash: one partial per 128-row block (no atomics)
         rsum = None if selfp else self._buf("r_colsum", (r_parts, C_pad), torch.float32, dev)
         ns = C.c_int(0)
@@ -520,8 +542,7 @@ class HeadEngine:
             xs = self._buf("xs", (B_pad, L.D), torch.bfloat16, dev)
             rho = self._buf("rho", (B_pad,), torch.float32, dev)
             gty = self._buf("gty", (B_pad,), torch.float32, dev)
-            L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
-                   _ptr(xs), _ptr(rho), _ptr(gty), st)
+            self._stash_prep(ctx, xs, rho, gty, st)
             if need_dx or not selfp:       # without self-projection the dx kernel's side pass also produces r_colsum
                 part = self._buf("dxhat_part", (n_split, B_pad, L.D), torch.float32, dev)
                 if selfp:
@@ -574,8 +595,7 @@ class HeadEngine:
             xs = self._buf("xs", (B_pad, L.D), torch.bfloat16, dev)
             rho = self._buf("rho", (B_pad,), torch.float32, dev)
             gty = self._buf("gty", (B_pad,), torch.float32, dev)
-            L.call("mh_stash_prep", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
-                   _ptr(xs), _ptr(rho), _ptr(gty), st)
+            self._stash_prep(ctx, xs, rho, gty, st)
         else:
             G = self._buf("G", (B_pad, C_pad), torch.bfloat16, dev)
             L.call("mh_tc_backward_g", C.byref(self.cfg), _ptr(x_hat), B, B_pad, _ptr(w_hat), Cn, C_pad, _ptr(rowp), B_pad,
@@ -600,6 +620,18 @@ class HeadEngine:
         else:
             dx = self._finish_dx(ctx, part, n_split, split_stride, gscal, aux0, aux1)
         return dx, dW
+
+    def _stash_prep(self, ctx, xs, rho, gty, st):
+        """rho_i, gty_i and the scaled rows of the stash backward.  Guarded stash: a gated backward-G launch first rewrites the
+        stash with the recomputed G when the forward raised the flag, and the prep kernel then uses rho = 1 / gty = 0."""
+        B, B_pad, C_pad, Cn = ctx["B"], ctx["B_pad"], ctx["C_pad"], self.C
+        rowp, rowout, guard = ctx["rowp"], ctx["rowout"], ctx.get("guard")
+        if guard is not None:
+            L.call("mh_tc_backward_g_ex", C.byref(self.cfg), _ptr(ctx["x_hat"]), B, B_pad, _ptr(ctx["w_hat"]), Cn, C_pad,
+                   _ptr(rowp), B_pad, _ptr(ctx["label_local"]), _ptr(ctx["state"]), _ptr(rowout[L.RO["LSE2"]]),
+                   _ptr(ctx["stash"]), _ptr(None), _ptr(guard), 1, st)
+        L.call("mh_stash_prep_ex", C.byref(self.cfg), _ptr(rowp), B_pad, _ptr(rowout), B_pad, _ptr(ctx["x_hat32"]), B, B_pad,
+               _ptr(xs), _ptr(rho), _ptr(gty), _ptr(guard), st)
 
     def _backward_vpl(self, ctx, gscal, need_dx, need_dw):
         """VPL-ArcFace backward on the stash: dx^ = diag(rho) E'.v + G_iy (1 - a_y) w^_y;  dw^_j = (1 - a_j) E'^T.(rho x^)

@@ -422,6 +422,37 @@ int mh_step_forward(const mh_config* cfg_host, const mh_step_ws* ws, const void*
 int mh_step_backward(const mh_config* cfg_host, const mh_step_ws* ws, int stash, const float* state,
                      const float* g_loss, const float* g_lossg, void* dx, float* dW, void* stream);
 
+/* ---- gated / guarded forms (the building blocks of the guarded stash, for drivers that sequence the kernels themselves:
+ * the class-sharded head puts collectives between them) ---------------------------------------------------------------
+ * gate: device flag read by every thread of the launch before anything else; the launch does nothing unless
+ * (*gate != 0) == (gate_on != 0).  gate == NULL: always runs (then each function equals its plain namesake). */
+
+/* mh_tc_forward with stash_kind: 0 no stash (stash_bf16 NULL), 1 the proven stash (mh_tc_stash_ok), 2 the guarded stash
+ * (mh_tc_stash_guarded_ok: fixed-reference sums + stash whose validity the caller checks with mh_finalize_rows_ex). */
+int mh_tc_forward_ex(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad, const void* w_hat_bf16,
+                     int64_t C, int64_t C_pad, const float* rowp, int64_t ldp, const int32_t* label_local,
+                     const float* state, float* stats_tiles, void* stash_bf16, int stash_kind, const int32_t* gate,
+                     int gate_on, void* stream);
+/* mh_tc_backward_g behind a gate (r_colsum must be NULL when gated). */
+int mh_tc_backward_g_ex(const mh_config* cfg_host, const void* x_hat_bf16, int64_t B, int64_t B_pad,
+                        const void* w_hat_bf16, int64_t C, int64_t C_pad, const float* rowp, int64_t ldp,
+                        const int32_t* label_local, const float* state, const float* lse2, void* G_bf16,
+                        float* r_colsum, const int32_t* gate, int gate_on, void* stream);
+/* mh_merge_stats behind a gate. */
+int mh_merge_stats_ex(const float* stats_in, int64_t n_parts, int64_t B, int64_t lds, float* scratch, float* stats_out,
+                      const int32_t* gate, int gate_on, void* stream);
+/* mh_finalize_rows behind a gate, and / or with the guard of the guarded stash: guard_flag != NULL also writes
+ * *guard_flag = 1 if any row's fixed-reference sum is below guard_min_l (= C_total * 2^-102: everything that can have been
+ * flushed to zero is then < 2^-24 of the sum), else 0. */
+int mh_finalize_rows_ex(const float* stats, int64_t lds, const float* rowp, int64_t ldp, int64_t B, int64_t B_total,
+                        int sphere, float* rowout, int64_t ldo, float* scalars, const float* state, float guard_min_l,
+                        int32_t* guard_flag, const int32_t* gate, int gate_on, void* stream);
+/* mh_stash_prep for the guarded stash: with *fallback != 0 (the forward fell back and mh_tc_backward_g_ex rewrote the
+ * B x C buffer with G itself) rho = 1, gty = 0 and xs = bf16(x^). */
+int mh_stash_prep_ex(const mh_config* cfg_host, const float* rowp, int64_t ldp, const float* rowout, int64_t ldo,
+                     const float* x_hat32, int64_t B, int64_t B_pad, void* xs_bf16, float* rho, float* gty,
+                     const int32_t* fallback, void* stream);
+
 /* ---- VPL-ArcFace (criterion.py:619-762) ------------------------------------------------------------------ */
 
 /* Mixed class vectors of the virtual-proxy head: with a_j = lamda * 1[life_j > 0] (life AFTER this step's decay,

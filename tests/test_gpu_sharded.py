@@ -31,10 +31,19 @@ def _worker(rank, world, port, fam, bmode, q):
         from tests.helpers import build_head, cosim, prime_head, rel
         Bl, Cn = 96, 5003                       # ragged last shard at 2 and at 8 ranks (2502/2501, 7 x 626 + 621)
         cfg = mo.HeadConfig.default(fam)
-        x, W, labels = mo.make_inputs(fam, Bl * world, Cn, 512, seed=77)
+        # "stash" on CurricularFace / SphereFace = the guarded stash (every rank derives the same flag from the merged
+        # statistics); "stash_adv": inputs built to underflow, so the gated general path must take over on every rank
+        adversarial = bmode == "stash_adv"
+        if adversarial:
+            from tests.test_gpu_guarded_stash import _inputs
+            x, W, labels = _inputs(fam, Bl * world, Cn, 77, True)
+            bmode = "stash"
+        else:
+            x, W, labels = mo.make_inputs(fam, Bl * world, Cn, 512, seed=77)
         ref = mo.loss_and_grads(cfg, mo.HeadState(), x, W, labels)
         kw = dict(arcface=dict(s=cfg.s, m=cfg.m, easy_margin=False), curricularface=dict(m=cfg.m, s=cfg.s, momentum=cfg.momentum),
-                  cosface=dict(s=cfg.s, m=cfg.m), mv_am=dict(margin=cfg.m, mv_weight=cfg.mv_weight, s=cfg.s))[fam]
+                  cosface=dict(s=cfg.s, m=cfg.m), mv_am=dict(margin=cfg.m, mv_weight=cfg.mv_weight, s=cfg.s),
+                  sphereface=dict(m=cfg.sphere_m))[fam]
         head = pkg.ShardedMarginHead(fam, Cn, **kw).cuda()
         head.engine.backward_mode = bmode
         b, e = head.c_begin, head.c_end
@@ -49,6 +58,8 @@ def _worker(rank, world, port, fam, bmode, q):
         torch.cuda.synchronize()
         assert abs(float(out.loss) - float(ref["loss"])) < 2e-3 * abs(float(ref["loss"]))
         assert abs(float(out.acc1) - float(ref["acc1"])) < 0.6
+        if bmode == "stash" and fam in ("curricularface", "sphereface"):
+            assert int(head.engine._ws["stash_guard"].item()) == (1 if adversarial else 0)
         dx_ref = ref["dx"][rank * Bl:(rank + 1) * Bl]
         dW_ref = ref["dW"][b:e] if mo.LAYOUT[fam] == "CD" else ref["dW"][:, b:e]
         assert cosim(xl.grad, dx_ref) > 0.9995 and cosim(head.shard_parameter().grad, dW_ref) > 0.9995
@@ -130,7 +141,8 @@ def test_head_on_non_current_device():
 
 @pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("fam,bmode", [("arcface", "auto"), ("arcface", "recompute"), ("curricularface", "auto"),
-                                       ("cosface", "auto"), ("mv_am", "auto")])
+                                       ("cosface", "auto"), ("mv_am", "auto"), ("curricularface", "stash"),
+                                       ("curricularface", "stash_adv"), ("sphereface", "stash")])
 def test_sharded_matches_oracle(fam, bmode, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -682,6 +682,7 @@ def run_b200(args):
             sampler.armed = False
         kern = {}
         for name, e0, e1, launches in prof:
+            name = name[:-3] if name.endswith("_ex") else name        # gated forms (guarded stash): same kernels
             k = kern.setdefault(name, [0.0, 0, 0])
             k[0] += e0.elapsed_time(e1)
             k[1] += 1 if launches else 0

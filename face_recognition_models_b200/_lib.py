@@ -38,7 +38,7 @@ class MhStepWs(C.Structure):
         ("rowout", C.c_void_p), ("bc", C.c_void_p), ("xs", C.c_void_p), ("rho", C.c_void_p), ("gty", C.c_void_p),
         ("dxhat_part", C.c_void_p), ("part_splits", C.c_int64), ("dxhat_full", C.c_void_p), ("gscal", C.c_void_p),
         ("r_colsum", C.c_void_p), ("rpart", C.c_void_p), ("rflag", C.c_void_p), ("dx_sync", C.c_void_p),
-        ("pw_ready", C.c_void_p), ("prog", C.c_void_p), ("guard", C.c_void_p),
+        ("pw_ready", C.c_void_p), ("prog", C.c_void_p), ("guard", C.c_void_p), ("graph_cache", C.c_void_p),
     ]
 
 
@@ -81,6 +81,9 @@ SIGNATURES = {
     "mh_pair_cosine": [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _vp],
     "mh_step_forward": [_cfgp, C.POINTER(MhStepWs), _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
     "mh_step_backward": [_cfgp, C.POINTER(MhStepWs), _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mh_step_cache_create": [C.POINTER(C.c_void_p)],
+    "mh_step_cache_destroy": [_vp],
+    "mh_step_cache_stats": [_vp, C.POINTER(C.c_int64)],
     "mh_tc_fixref_ok": [_cfgp, _i64],
     "mh_tc_stash_ok": [_cfgp, _i64],
     "mh_tc_stash_guarded_ok": [_cfgp, _i64],

@@ -21,9 +21,9 @@ static int check_ws(const mh_step_ws* ws) {
   return MH_OK;
 }
 
-extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const void* x, const int64_t* labels,
-                               const float* W, const float* margins, float* state, int update_state, int run_prologue_w,
-                               int stash, float* scalars, void* stream) {
+static int step_forward_body(const mh_config* cfg, const mh_step_ws* ws, const void* x, const int64_t* labels,
+                             const float* W, const float* margins, float* state, int update_state, int run_prologue_w,
+                             int stash, float* scalars, void* stream) {
   MH_CHECK_ARG(cfg && x && labels && W && state && scalars, "null pointer");
   STEP_TRY(check_ws(ws));
   MH_CHECK_ARG(!stash || ws->bc, "stash requested without a B x C buffer");
@@ -71,8 +71,8 @@ extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const
   return MH_OK;
 }
 
-extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int stash, const float* state,
-                                const float* g_loss, const float* g_lossg, void* dx, float* dW, void* stream) {
+static int step_backward_body(const mh_config* cfg, const mh_step_ws* ws, int stash, const float* state,
+                              const float* g_loss, const float* g_lossg, void* dx, float* dW, void* stream) {
   MH_CHECK_ARG(cfg && state, "null pointer");
   STEP_TRY(check_ws(ws));
   MH_CHECK_ARG(ws->bc && ws->gscal && ws->dxhat_part, "null backward workspace pointer");
@@ -168,4 +168,204 @@ extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int 
                                   ws->layout, dW, ws->ld, stream));
   }
   return MH_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Graph replay of a phase.  A phase is 7-12 dependent launches, most of them a few microseconds long; at BASELINE
+// configs 2 and 3 the gaps between them and the host time to issue them are a large part of the step.  When the caller
+// hands in a cache (ws->graph_cache, mh_step_cache_create), a phase is captured the first time a set of arguments
+// (hyper-parameters, workspace descriptor, every pointer and flag, compared byte by byte) is seen -- on the cache's
+// private stream, so the caller's stream may be the legacy default stream -- and replayed with ONE cudaGraphLaunch on
+// the caller's stream whenever that set comes back: same kernels, same arguments, same order, hence the same bits.  Any change of
+// an argument (a fresh output tensor at another address, SphereFace's annealed lambda) is just a different key; the
+// cache holds a few keys (LRU), and a phase whose key keeps changing falls back to plain launches for a while instead
+// of re-capturing every step.  A caller that is itself capturing (tests/test_gpu_graph.py) gets plain launches, which
+// its own capture records.  MH_STEP_GRAPH=0 disables the mechanism.
+// ------------------------------------------------------------------------------------------------------------------
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace {
+
+struct PhaseKey {
+  mh_config cfg;
+  mh_step_ws ws;
+  const void* p[8];
+  int i[4];
+};
+
+struct PhaseEntry {
+  PhaseKey key;
+  cudaGraphExec_t exec;
+  uint64_t last_use;
+};
+
+struct PhaseCache {
+  std::vector<PhaseEntry> entries;
+  int misses_in_row = 0;
+  int64_t cool_down = 0;          // calls left during which this phase does not try to capture
+};
+
+constexpr int kMaxEntries = 6;
+constexpr int kMissLimit = 6;      // captures in a row without a hit before the phase backs off
+constexpr int kCoolDown = 200;
+
+}  // namespace
+
+struct mh_step_cache_s {
+  std::mutex mu;
+  int device = -1;
+  cudaStream_t cap_stream = nullptr;
+  uint64_t tick = 0;
+  int64_t n_replay = 0, n_capture = 0, n_plain = 0;
+  PhaseCache phase[2];             // 0 forward, 1 backward
+};
+
+static bool step_graphs_enabled() {
+  static const bool on = [] { const char* e = getenv("MH_STEP_GRAPH"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+extern "C" int mh_step_cache_create(void** out) {
+  MH_CHECK_ARG(out, "null pointer");
+  mh_step_cache_s* c = new mh_step_cache_s();
+  MH_CUDA_OK(cudaGetDevice(&c->device));
+  cudaError_t e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    mh_set_error("mh_step_cache_create: cudaStreamCreateWithFlags -> %s", cudaGetErrorString(e));
+    return MH_ERR_CUDA;
+  }
+  *out = c;
+  return MH_OK;
+}
+
+extern "C" int mh_step_cache_destroy(void* cache) {
+  if (!cache) return MH_OK;
+  mh_step_cache_s* c = static_cast<mh_step_cache_s*>(cache);
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int ph = 0; ph < 2; ++ph) {
+      for (PhaseEntry& en : c->phase[ph].entries) cudaGraphExecDestroy(en.exec);
+      c->phase[ph].entries.clear();
+    }
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    c->cap_stream = nullptr;
+  }
+  delete c;
+  return MH_OK;
+}
+
+extern "C" int mh_step_cache_stats(void* cache, int64_t* counts3) {
+  MH_CHECK_ARG(cache && counts3, "null pointer");
+  mh_step_cache_s* c = static_cast<mh_step_cache_s*>(cache);
+  std::lock_guard<std::mutex> lk(c->mu);
+  counts3[0] = c->n_replay;
+  counts3[1] = c->n_capture;
+  counts3[2] = c->n_plain;
+  return MH_OK;
+}
+
+// Runs `body(stream)` either directly or through the cache.  Returns the body's status (a failed capture falls back to
+// direct launches; only the direct run's status is reported).
+template <class Body>
+static int run_phase(void* cache_v, int ph, const PhaseKey& key, void* stream, Body&& body) {
+  mh_step_cache_s* c = static_cast<mh_step_cache_s*>(cache_v);
+  if (!c || !step_graphs_enabled()) return body(stream);
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != c->device) return body(stream);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing((cudaStream_t)stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return body(stream);                                   // the caller is capturing: let its capture record the launches
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  PhaseCache& pc = c->phase[ph];
+  ++c->tick;
+  for (PhaseEntry& en : pc.entries) {
+    if (memcmp(&en.key, &key, sizeof(PhaseKey)) == 0) {
+      en.last_use = c->tick;
+      pc.misses_in_row = 0;
+      ++c->n_replay;
+      MH_CUDA_OK(cudaGraphLaunch(en.exec, (cudaStream_t)stream));
+      return MH_OK;
+    }
+  }
+  // unknown key: capture it now, unless this phase keeps producing new keys (fresh addresses or hyper-parameters on
+  // every call): after kMissLimit captures in a row without a single hit it issues plain launches for kCoolDown calls
+  if (pc.cool_down > 0) {
+    --pc.cool_down;
+    ++c->n_plain;
+    return body(stream);
+  }
+  if (pc.misses_in_row >= kMissLimit) {
+    pc.misses_in_row = 0;
+    pc.cool_down = kCoolDown;
+    ++c->n_plain;
+    return body(stream);
+  }
+  ++pc.misses_in_row;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+  if (ok) {
+    const int rc = body((void*)c->cap_stream);
+    const cudaError_t ee = cudaStreamEndCapture(c->cap_stream, &graph);
+    ok = rc == MH_OK && ee == cudaSuccess && graph != nullptr;
+  }
+  if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();
+    pc.cool_down = kCoolDown;                               // something in this phase does not capture: plain launches
+    ++c->n_plain;
+    return body(stream);
+  }
+  if ((int)pc.entries.size() >= kMaxEntries) {
+    size_t lru = 0;
+    for (size_t k = 1; k < pc.entries.size(); ++k)
+      if (pc.entries[k].last_use < pc.entries[lru].last_use) lru = k;
+    cudaGraphExecDestroy(pc.entries[lru].exec);
+    pc.entries.erase(pc.entries.begin() + (long)lru);
+  }
+  PhaseEntry en;
+  en.key = key;
+  en.exec = exec;
+  en.last_use = c->tick;
+  pc.entries.push_back(en);
+  ++c->n_capture;
+  MH_CUDA_OK(cudaGraphLaunch(exec, (cudaStream_t)stream));
+  return MH_OK;
+}
+
+extern "C" int mh_step_forward(const mh_config* cfg, const mh_step_ws* ws, const void* x, const int64_t* labels,
+                               const float* W, const float* margins, float* state, int update_state, int run_prologue_w,
+                               int stash, float* scalars, void* stream) {
+  if (!cfg || !ws || !ws->graph_cache)
+    return step_forward_body(cfg, ws, x, labels, W, margins, state, update_state, run_prologue_w, stash, scalars, stream);
+  PhaseKey key;
+  memset(&key, 0, sizeof(key));
+  key.cfg = *cfg;
+  key.ws = *ws;
+  key.p[0] = x; key.p[1] = labels; key.p[2] = W; key.p[3] = margins; key.p[4] = state; key.p[5] = scalars;
+  key.i[0] = update_state; key.i[1] = run_prologue_w; key.i[2] = stash;
+  return run_phase(ws->graph_cache, 0, key, stream, [&](void* st) {
+    return step_forward_body(cfg, ws, x, labels, W, margins, state, update_state, run_prologue_w, stash, scalars, st);
+  });
+}
+
+extern "C" int mh_step_backward(const mh_config* cfg, const mh_step_ws* ws, int stash, const float* state,
+                                const float* g_loss, const float* g_lossg, void* dx, float* dW, void* stream) {
+  if (!cfg || !ws || !ws->graph_cache) return step_backward_body(cfg, ws, stash, state, g_loss, g_lossg, dx, dW, stream);
+  PhaseKey key;
+  memset(&key, 0, sizeof(key));
+  key.cfg = *cfg;
+  key.ws = *ws;
+  key.p[0] = state; key.p[1] = g_loss; key.p[2] = g_lossg; key.p[3] = dx; key.p[4] = dW;
+  key.i[0] = stash;
+  return run_phase(ws->graph_cache, 1, key, stream, [&](void* st) {
+    return step_backward_body(cfg, ws, stash, state, g_loss, g_lossg, dx, dW, st);
+  });
 }

@@ -129,6 +129,7 @@ class HeadEngine:
         self._shadow = None             # (W.data_ptr(), W._version, w_hat.data_ptr()) when sgd_step left a valid w_hat behind
         self._shadow_once = False       # set by prefetch_w: good for the next forward only (never a cross-step cache)
         self.vpl = None                 # VPLArcFace: dict(mem, life, lamda) set by the head before each forward
+        self._graph_cache = None        # handle of mh_step_cache_create (CUDA-graph replay of the two phases)
         self._step_key = None           # cached mh_step_ws descriptor of the whole-phase entry points (see _forward_step)
         self._step_ws = self._step_T = None
         self._stash_ok_key = None
@@ -158,6 +159,37 @@ class HeadEngine:
         self._ws.clear()
         self._shadow = None
         self._step_key = self._step_ws = self._step_T = None
+        self._drop_graph_cache()
+
+    def _graph_cache_handle(self):
+        """CUDA-graph cache of the two phases (mh_step_cache_create): the whole-phase entry points replay a phase whose
+        arguments they have seen before with one cudaGraphLaunch.  MH_STEP_GRAPH=0 keeps plain launches."""
+        if os.environ.get("MH_STEP_GRAPH", "1") == "0":
+            return None
+        if self._graph_cache is None:
+            h = C.c_void_p(0)
+            L.call("mh_step_cache_create", C.byref(h))
+            self._graph_cache = h
+        return self._graph_cache.value
+
+    def graph_stats(self):
+        """(replayed, captured, plain) phase counts of this engine's CUDA-graph cache, or None without one."""
+        if self._graph_cache is None:
+            return None
+        out = (C.c_int64 * 3)()
+        L.call("mh_step_cache_stats", self._graph_cache, out)
+        return tuple(int(v) for v in out)
+
+    def _drop_graph_cache(self):
+        h, self._graph_cache = getattr(self, "_graph_cache", None), None
+        if h is not None and h.value:
+            try:
+                L.call("mh_step_cache_destroy", h)
+            except Exception:                                   # interpreter shutdown: the library may already be gone
+                pass
+
+    def __del__(self):
+        self._drop_graph_cache()
 
     def _stash_ok_cached(self) -> bool:
         """stash_ok() depends only on the hyper-parameters, the shard size and backward_mode: asked once per change."""
@@ -416,7 +448,8 @@ class HeadEngine:
         Cn = self.C
         stash = self._stash_kind(B_pad, C_pad) if want_grad else 0        # 0 none / recompute, 1 stash, 2 guarded stash
         guarded = stash == 2
-        key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj(), _merged_bwd(), _merged_fwd())
+        key = (B, x.dtype, dev, ld, bool(want_grad), stash, _selfproj(), _merged_bwd(), _merged_fwd(),
+               os.environ.get("MH_STEP_GRAPH", "1"))
         if self._step_key != key:
             lib = L.load()
             n_tiles = int(lib.mh_fwd_num_tiles(C_pad))
@@ -461,6 +494,7 @@ class HeadEngine:
                              gty=b("gty", (B_pad,), torch.float32, dev),
                              dxhat_full=b("dxhat_full", (1, B_pad, L.D), torch.float32, dev))
             ws = L.MhStepWs()
+            ws.graph_cache = self._graph_cache_handle()
             ws.B, ws.B_pad, ws.C, ws.C_pad, ws.ld = B, B_pad, Cn, C_pad, ld
             ws.layout, ws.x_dtype = self.layout, _DT[x.dtype]
             ws.n_tiles, ws.part_splits = n_tiles, part_splits

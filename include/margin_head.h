@@ -394,7 +394,24 @@ typedef struct mh_step_ws {
                                   (mh_tc_backward_dxdw) whenever both gradients are wanted and the shape is eligible */
   int32_t* guard;              /* [1] or NULL; needed by the guarded stash (stash == 2): 1 after a forward whose fixed-reference
                                   sums could not be trusted and that therefore re-ran the general path on the device */
+  void* graph_cache;           /* handle from mh_step_cache_create or NULL: a phase is captured into a CUDA graph per distinct
+                                  argument set and replayed whenever that set comes back (see below) */
 } mh_step_ws;
+
+/* CUDA-graph cache of the two phases (HOST object, tied to the device that is current at creation).  mh_step_forward /
+ * mh_step_backward called with ws->graph_cache set capture a phase the first time they see a set of arguments
+ * (hyper-parameters, workspace descriptor, every pointer and flag, byte by byte) and replay it with one cudaGraphLaunch on
+ * the caller's stream whenever the same set comes back; the capture happens on a private stream of the cache, so the
+ * caller's stream may be the legacy default stream.  A few keys are kept (LRU); a phase whose key changes on every call
+ * (fresh addresses, SphereFace's annealed lambda) backs off to plain launches.  A caller
+ * whose stream is itself being captured gets plain launches.  Same kernels, arguments and order as without the cache:
+ * bit-identical results.  Thread-safe; destroy only when no call is in flight.  MH_STEP_GRAPH=0 in the environment
+ * disables replay. */
+int mh_step_cache_create(void** cache_out);
+int mh_step_cache_destroy(void* cache);
+/* counts3 = {phases replayed from a graph, phases captured (and then launched as a graph), phases issued as plain
+ * launches while backing off}; phases of a caller that is itself capturing are not counted. */
+int mh_step_cache_stats(void* cache, int64_t* counts3);
 
 /* Forward of one step: mh_prologue_w (skipped when run_prologue_w == 0: w_hat / inv_norm already hold this W, e.g.
  * after mh_sgd_step_w), mh_prologue_x, mh_row_params, mh_tc_forward (stashing into ws->bc when stash != 0; stash == 1

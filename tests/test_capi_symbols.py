@@ -63,7 +63,7 @@ def test_step_workspace_struct_mirrors_the_header():
             fields.append((n.strip().lstrip("*"), 4 if base == "int32_t" and "*" not in n and not base.endswith("*") else 8))
     assert [f[0] for f in fields] == [f[0] for f in _lib.MhStepWs._fields_]
     assert [f[1] for f in fields] == [ctypes.sizeof(f[1]) for f in _lib.MhStepWs._fields_]
-    assert fields[-1][0] == "guard"
+    assert fields[-1][0] == "graph_cache"
 
 
 def test_stash_eligibility_predicates(lib):

@@ -801,6 +801,9 @@ class FusedMarginLossFn(torch.autograd.Function):
         ctx.engine = engine
         ctx.c = c
         ctx.x_dtype = x.dtype
+        # undefined upstream gradients arrive as None instead of freshly filled zero tensors (four fill launches per step
+        # for loss_g / acc1 / acc5 / norms when only `loss` is differentiated); the C ABI takes NULL for "zero"
+        ctx.set_materialize_grads(False)
         loss, acc1, acc5, loss_g = c["scalars"].unbind(0)           # views of a tensor created by this forward
         norms = c["rowp"][L.RP["NORMS"], :c["B"]].clone().unsqueeze(1)
         ctx.mark_non_differentiable(norms, acc1, acc5)
@@ -809,10 +812,8 @@ class FusedMarginLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_lossg, _ga1, _ga5, _gn):
         eng = ctx.engine
-        if g_loss is None:
-            g_loss = torch.zeros((), device=ctx.c["x_hat"].device)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dx, dW = eng.backward(ctx.c, g_loss, g_lossg, need_dx, need_dw)
+        dx, dW = eng.backward(ctx.c, g_loss, g_lossg, need_dx, need_dw)       # None = zero upstream gradient (NULL in the C ABI)
         return dx, dW, None, None, None, None, None, None, ctx.c.get("dt_ext")
 
 
@@ -824,6 +825,7 @@ class DenseMarginLogitsFn(torch.autograd.Function):
         c = engine.forward(x, W, labels, state, margins, update_state=update_state, want_dense=True)
         ctx.engine = engine
         ctx.c = c
+        ctx.set_materialize_grads(False)
         norms = c["rowp"][L.RP["NORMS"], :c["B"]].clone().unsqueeze(1)
         loss_g = state[3].clone()
         ctx.mark_non_differentiable(norms)

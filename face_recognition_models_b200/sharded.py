@@ -100,6 +100,7 @@ class _ShardedFusedLossFn(torch.autograd.Function):
         ctx.engine = engine
         ctx.head = head
         ctx.c = c
+        ctx.set_materialize_grads(False)        # None instead of zero-filled tensors for the outputs nobody differentiates
         ctx.B_local = x_local.shape[0]
         sc = c["scalars"]
         r0 = comm.rank * ctx.B_local
@@ -111,8 +112,6 @@ class _ShardedFusedLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_lossg, _a1, _a5, _n):
         head = ctx.head
-        if g_loss is None:
-            g_loss = torch.zeros((), device=ctx.c["x_hat"].device)
         dx, dW = ctx.engine.backward(ctx.c, g_loss, g_lossg, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         if dx is not None and head.dx_scale != 1.0:
             dx = dx * head.dx_scale

@@ -8,7 +8,10 @@ Two execution paths, both CUDA only (there is no CPU / PyTorch fallback):
               ``stash``     - the forward additionally writes the unnormalised probabilities
                               E' = exp2(z - ref) du/dcos in bf16 (fixed softmax reference), and the backward
                               runs only the two gradient GEMMs (3 instead of 4 GEMM passes per step).
-              ``auto`` (default) = stash whenever ``mh_tc_fixref_ok`` holds for the head, else recompute.
+              ``auto`` (default) = stash whenever ``mh_tc_stash_ok`` holds for the head; else, at scale, the GUARDED
+                              stash (``mh_tc_stash_guarded_ok``: CurricularFace, SphereFace, s > 69 -- the same
+                              forward + stash run speculatively, a device-side check of the row sums, and the
+                              general path behind it as gated launches); else recompute.
 * ``exact`` - fp32 SIMT path that materialises the cosine matrix (small C: fp32-tolerance mode,
               and the compat mode returning the reference's 4-tuple).
 

@@ -230,14 +230,14 @@ static bool step_graphs_enabled() {
 
 extern "C" int mh_step_cache_create(void** out) {
   MH_CHECK_ARG(out, "null pointer");
+  *out = nullptr;
+  int dev = -1;
+  MH_CUDA_OK(cudaGetDevice(&dev));
+  cudaStream_t cap = nullptr;
+  MH_CUDA_OK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
   mh_step_cache_s* c = new mh_step_cache_s();
-  MH_CUDA_OK(cudaGetDevice(&c->device));
-  cudaError_t e = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) {
-    delete c;
-    mh_set_error("mh_step_cache_create: cudaStreamCreateWithFlags -> %s", cudaGetErrorString(e));
-    return MH_ERR_CUDA;
-  }
+  c->device = dev;
+  c->cap_stream = cap;
   *out = c;
   return MH_OK;
 }

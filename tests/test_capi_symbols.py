@@ -87,6 +87,22 @@ def test_stash_eligibility_predicates(lib):
         assert lib.mh_tc_stash_guarded_ok(ctypes.byref(c), 1) == 0
 
 
+def test_graph_cache_entry_points_fail_cleanly_without_a_gpu(lib):
+    """mh_step_cache_create needs a CUDA device; without one it must report an error (no crash, no handle), and destroying
+    a NULL handle is a no-op."""
+    import torch
+    h = ctypes.c_void_p(0)
+    st = lib.mh_step_cache_create(ctypes.byref(h))
+    if torch.cuda.is_available():
+        assert st == 0 and h.value
+        counts = (ctypes.c_int64 * 3)()
+        assert lib.mh_step_cache_stats(h, counts) == 0 and list(counts) == [0, 0, 0]
+        assert lib.mh_step_cache_destroy(h) == 0
+    else:
+        assert st != 0 and not h.value and b"mh_step_cache_create" in lib.mh_last_error()
+    assert lib.mh_step_cache_destroy(None) == 0
+
+
 def test_version_and_error_strings(lib):
     assert b"sm_100a" in lib.mh_version()
     assert isinstance(lib.mh_last_error(), bytes)

@@ -139,6 +139,18 @@ class HeadEngine:
         # "auto" | "stash" | "recompute"; MH_BACKWARD in the environment overrides (A/B measurements)
         self.backward_mode = os.environ.get("MH_BACKWARD", "auto")
 
+    # copy.deepcopy(head) (EMA copies, checkpoints of the module object) and pickling: the copy keeps the hyper-parameters
+    # and modes but none of the device workspaces, raw-pointer descriptors or the CUDA-graph cache of the original (they
+    # would alias the original's buffers, and the cache handle would be destroyed twice); it rebuilds its own on first use
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.update(_ws={}, _shadow=None, _shadow_once=False, _step_key=None, _step_ws=None, _step_T=None, _graph_cache=None,
+                 _stash_ok_key=None, vpl=None, _gen=0)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+
     def stash_ok(self) -> bool:
         """True when the forward may stash E' for the backward (fixed-reference softmax applies)."""
         if self.mode != "tc" or self.backward_mode == "recompute":

@@ -174,3 +174,26 @@ def test_partial_fc_sampling_keeps_positives_and_remaps_labels():
     idx, ys = small.sample_classes(y_many)
     kept = torch.isin(y_many, idx)
     assert int(kept.sum()) == 10 and bool((ys[~kept] == 10).all()) and torch.equal(idx[ys[kept]], y_many[kept])
+
+
+def test_deepcopy_of_a_head_drops_workspaces_and_graph_cache():
+    """copy.deepcopy(head) (EMA copies): the copy must not alias the original's device workspaces, raw-pointer step
+    descriptor or CUDA-graph cache handle (double destroy); hyper-parameters, modes and parameters are copied."""
+    import copy
+    import ctypes
+    import torch
+    import face_recognition_models_b200 as pkg
+    head = pkg.CurricularFace(512, 100, m=0.4, s=48.0)
+    head.backward_mode = "recompute"
+    eng = head._engine
+    eng._ws["probe"] = torch.zeros(3)                    # stand-ins for state a forward would have left behind
+    eng._graph_cache = ctypes.c_void_p(0)                # NULL handle: destroy is a no-op, but the copy must not share it
+    eng._step_key = ("k",)
+    eng._shadow = (1, 2, 3)
+    dup = copy.deepcopy(head)
+    d = dup._engine
+    assert d is not eng and d._ws == {} and d._graph_cache is None and d._step_key is None and d._shadow is None
+    assert d.family == eng.family and d.C == eng.C and d.backward_mode == "recompute"
+    assert abs(d.cfg.s - 48.0) < 1e-6 and abs(d.cfg.m - 0.4) < 1e-6 and d.cfg is not eng.cfg
+    assert torch.equal(dup.kernel, head.kernel) and dup.kernel.data_ptr() != head.kernel.data_ptr()
+    assert "probe" in eng._ws                            # the original keeps its own

@@ -197,3 +197,31 @@ def test_deepcopy_of_a_head_drops_workspaces_and_graph_cache():
     assert abs(d.cfg.s - 48.0) < 1e-6 and abs(d.cfg.m - 0.4) < 1e-6 and d.cfg is not eng.cfg
     assert torch.equal(dup.kernel, head.kernel) and dup.kernel.data_ptr() != head.kernel.data_ptr()
     assert "probe" in eng._ws                            # the original keeps its own
+
+
+def test_backward_mode_selection_is_host_logic(monkeypatch):
+    """Which backward a head takes (0 recompute / 1 proven stash / 2 guarded stash) is decided on the host from the
+    hyper-parameters, the padded shape and backward_mode: no device needed."""
+    import face_recognition_models_b200 as pkg
+    from face_recognition_models_b200.functional import GUARDED_MIN_BC
+    monkeypatch.delenv("MH_STASH_GUARDED", raising=False)
+    big = (1024, 2_000_128)                                        # cfg4's padded shape
+    small = (512, 10_752)                                          # cfg2's
+    assert small[0] * small[1] < GUARDED_MIN_BC <= big[0] * big[1]
+    arc = pkg.ArcFace(512, 1000)._engine
+    assert arc._stash_kind(*small) == 1 and arc._stash_kind(*big) == 1
+    arc.backward_mode = "recompute"
+    assert arc._stash_kind(*big) == 0
+    for head in (pkg.CurricularFace(512, 1000), pkg.SphereFace(512, 1000, m=2), pkg.ArcFace(512, 1000, s=128.0)):
+        e = head._engine
+        assert e._stash_kind(*small) == 0 and e._stash_kind(*big) == 2          # auto: guarded stash at scale only
+        e.backward_mode = "stash"
+        assert e._stash_kind(*small) == 2                                        # forced: at any size
+        e.backward_mode = "recompute"
+        assert e._stash_kind(*big) == 0
+        e.backward_mode = "auto"
+        monkeypatch.setenv("MH_STASH_GUARDED", "0")
+        assert e._stash_kind(*big) == 0
+        monkeypatch.delenv("MH_STASH_GUARDED")
+    mv = pkg.MV_Softmax(512, 1000, margin=0.35, mv_weight=1.12, s=32.0, margin_type="am")._engine
+    assert mv._stash_kind(*small) == 1
